@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- schema-head images/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA head
+    python bench.py --impl reference --gpus N ...            # the reference's CPU head on the box's host cores
+
+A "step" is one pass of the whole head (discretize -> instance graphs -> class atlas -> class-side GNN ->
+instance-side GNN -> logits) over one batch of synthetic tensors of the DeiT-Small / CIFAR-100 shape
+(BASELINE.json configs[1]; B=256 per GPU, d=384, M=1024, K=100, Vc=1024, D=256).  The class side is recomputed every
+step, as the reference does.  N > 1: one process per GPU, the batch is sharded (weak scaling: 256 images per GPU), no
+data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "schemanet-pytorch_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOAD = "cfg2"
+L = 196
+N_INPUT_SETS = 3      # distinct input batches rotated between steps (plus 419 MB of class edges streamed per step)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.thread, self.gpu = [], None, None, str(gpu_index)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", self.gpu], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_problem(cfg, seed, device):
+    """Seeded synthetic tensors of SURVEY.md section 8d, built on the CPU (identical for the GPU and CPU arms)."""
+    import head_oracle as ho
+    c = ho.CONFIGS[cfg]
+    vocab = None
+    sets = []
+    for i in range(N_INPUT_SETS):
+        vocab, mid, attn, attn_cls = ho.synth_inputs(c["B"], c["d"], c["M"], seed + 10 * i, L, "easy", vocab)
+        sets.append((mid, attn, attn_cls))
+    schema = ho.synth_schema(c["M"], c["K"], c["Vc"], seed + 1)
+    gnn = ho.synth_gnn(c["M"], c["D"], seed + 2)
+    return c, vocab, sets, schema, gnn
+
+
+def build_head(c, vocab, schema, gnn, device):
+    from schema_inference.graph import SchemaNet, Matcher
+    from schemanet_b200.head import SchemaHead
+    import head_oracle as ho
+    sn = SchemaNet(c["M"], c["K"], class_max_vertices=c["Vc"], clamp_vertex_attn=ho.HEAD_CFG["clamp_vertex_attn"],
+                   clamp_edge_attn=ho.HEAD_CFG["clamp_edge_attn"], prune_node_threshold=ho.HEAD_CFG["prune_node_threshold"])
+    sn.vertex_weights.copy_(schema["vertex_weights"])
+    sn.edge_weights.copy_(schema["edge_weights"])
+    sn.vertex_attribute_weights.copy_(schema["w_v"])
+    sn.edge_attribute_weights.copy_(schema["w_e"])
+    sn.register_class_vertices(schema["class_ingredients"])
+    m = Matcher("inner_product", c["M"], dict(embed_dim=c["D"], num_layers=2, identity_proj=False, activation="relu"))
+    m.gnn.load_state_dict(gnn)
+    sn.to(device).eval()
+    m.to(device).eval()
+    return SchemaHead(vocab.to(device), sn, m)
+
+
+def cpu_head_time(c, vocab, sets, schema, gnn, iters, batch=None):
+    """The reference head on host cores: the reference's own C++ (oracle/_ref) for the native loops when it was built,
+    the oracle's restatement (same ATen CPU ops the reference calls) for the Python parts."""
+    import head_oracle as ho
+    import build_ref
+    ext = build_ref.load()
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    mid, attn, attn_cls = sets[0]
+    B = batch or c["B"]
+    mid, attn, attn_cls = mid[:, :B].contiguous(), attn[:B].contiguous(), attn_cls[:B].contiguous()
+    times = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        ho.head_forward(mid, attn, attn_cls, vocab, schema, gnn, ho.HEAD_CFG, ext=ext)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return B / med, med, cores, ("reference" if ext is not None else "port")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c, vocab, sets, schema, gnn = make_problem(WORKLOAD, 1234, "cpu")
+    B = c["B"]      # bounded sample: the full 256-image batch, at most 5 timed steps (~2-3 s each on 8 cores)
+    cpu_head_time(c, vocab, sets, schema, gnn, 1, batch=B)
+    t0 = time.perf_counter()
+    ips, med, cores, kind = cpu_head_time(c, vocab, sets, schema, gnn, max(1, min(args.steps, 5)), batch=B)
+    sample = (f"full {B}-image cfg2 batch per step, K={c['K']} class side recomputed per step, 1 warm-up + "
+              f"{max(1, min(args.steps, 5))} timed steps; native loops = {'reference C++ (oracle/_ref)' if kind == 'reference' else 'oracle C restatement'},"
+              f" ATen CPU ops for cdist/bmm/linear/layer_norm with {cores} threads; median of the timed steps")
+    line = {"impl": "reference", "metric": "schema_head_images_per_sec", "value": ips, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(c, args.gpus),
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(c, n_gpus):
+    return {"workload": "DeiT-Small SchemaNet head, CIFAR-100 shape (BASELINE.json configs[1])", "batch_per_gpu": c["B"],
+            "global_batch": c["B"] * n_gpus, "tokens": L, "d": c["d"], "vocab_M": c["M"], "classes_K": c["K"],
+            "class_vertices_Vc": c["Vc"], "gnn_dim_D": c["D"], "parallelism": f"batch-shard dp{n_gpus}",
+            "class_side": "recomputed every step (reference semantics)",
+            "cache_policy": "3 rotating input sets (116 MB each) + 419 MB class edges streamed per step: larger than "
+                            "the 126 MB L2"}
+
+
+def stage_bytes_flops(c, n_bar):
+    """Algorithmic bytes / flops per step of each stage."""
+    B, d, M, K, Vc, D = c["B"], c["d"], c["M"], c["K"], c["Vc"], c["D"]
+    return {
+        "discretize": {"flops": 2.0 * L * B * d * M, "bytes": B * (L * d * 4 + L * 8) + M * d * 4},
+        "graph_build": {"bytes": B * (L * L * 4 + L * 4 + L * 8 + 4 * n_bar * n_bar + 12 * n_bar + 8) + L * L * 4},
+        "atlas": {"bytes": 2.0 * K * Vc * Vc * 4 + 2.0 * K * Vc * 4},
+        "class_adj_gemm": {"flops": 2.0 * K * Vc * Vc * D, "bytes": K * (Vc * Vc * 4 + 2 * Vc * D * 4)},   # per layer
+        "class_gnn": {"flops": 2.0 * K * (2.0 * Vc * Vc * D + 2.0 * Vc * D * D)},
+        "instance_gnn": {"flops": B * 2.0 * (2.0 * n_bar * n_bar * D + 2.0 * n_bar * D * D)},
+    }
+
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from schemanet_b200 import native
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    native.lib()
+    c, vocab, sets, schema, gnn = make_problem(WORKLOAD, 1234 + rank, dev)
+    head = build_head(c, vocab, schema, gnn, dev)
+    dev_sets = [tuple(t.to(dev) for t in s) for s in sets]
+    pinned = [tuple(t.pin_memory() for t in s) for s in sets]
+    stage_in = tuple(torch.empty_like(t, device=dev) for t in sets[0])
+    pred_host = torch.empty(c["B"], c["K"], dtype=torch.float32).pin_memory()
+
+    def step(i):
+        mid, attn, attn_cls = dev_sets[i % N_INPUT_SETS]
+        return head(mid, attn, attn_cls)
+
+    def step_e2e(i):
+        hm, ha, hc = pinned[i % N_INPUT_SETS]
+        stage_in[0].copy_(hm, non_blocking=True)
+        stage_in[1].copy_(ha, non_blocking=True)
+        stage_in[2].copy_(hc, non_blocking=True)
+        out = head(*stage_in)
+        pred_host.copy_(out["pred"], non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = native.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = native.launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches
+
+    W = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step, args.steps, W)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps, W)
+
+    images = c["B"] * world * args.steps
+    value = images / (ms * 1e-3)
+    e2e_value = images / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in sets[0])
+    d2h = pred_host.numel() * 4
+
+    line = None
+    if rank == 0:
+        # per-kernel CUDA-event timings over a further K steps of the same workload (events on the launching stream)
+        out = step(0)
+        n_bar = float(out["graphs"].num_vertices.float().mean())
+        native.profile_enable(True)
+        for i in range(args.steps):
+            step(i)
+        prof = native.profile_collect()
+        native.profile_enable(False)
+        peaks = load_peaks()
+        alg = stage_bytes_flops(c, n_bar)
+        kern = {k: {"launches": v[0], "ms_total": v[1], "ms_per_launch": v[1] / max(v[0], 1)} for k, v in prof.items()}
+        total_prof = sum(v[1] for v in prof.values())
+        for k in kern:
+            kern[k]["share"] = kern[k]["ms_total"] / total_prof if total_prof else None
+        dom = max(prof.items(), key=lambda kv: kv[1][1])[0]
+        roof = None
+        if dom == "gnn_adj_gemm":
+            # launches alternate class side (K graphs of Vc nodes) and instance side; the class-side launches dominate.
+            # achieved = algorithmic flops of ALL adjacency-GEMM launches in a step / their summed duration
+            per_step_flops = 2 * alg["class_adj_gemm"]["flops"] + c["B"] * 2 * 2.0 * n_bar * n_bar * c["D"]
+            ach = per_step_flops * args.steps / (kern[dom]["ms_total"] * 1e-3) / 1e12
+            peak = peaks["bf16_tflops_sustained"] / 2     # TF32 tensor peak ~ half the measured BF16 peak
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peaks["source"] + " bf16 sustained / 2 (TF32-equivalent)",
+                    "note": "fp32 CUDA-core FMA path this round; see DESIGN.md for the tcgen05 3xTF32 plan"}
+        else:
+            key = {"discretize_exact_kernel": "discretize", "instance_graph_kernel": "graph_build",
+                   "class_edges_kernel": "atlas"}.get(dom)
+            if key and "bytes" in alg[key] and key != "discretize":
+                ach = alg[key]["bytes"] * args.steps / (kern[dom]["ms_total"] * 1e-3) / 1e9
+                roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+            elif key == "discretize":
+                ach = alg[key]["flops"] * args.steps / (kern[dom]["ms_total"] * 1e-3) / 1e12
+                peak = peaks["bf16_tflops_sustained"] / 2
+                roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + " bf16 sustained / 2"}
+        stages = {}
+        hbm = peaks["hbm_gbs"]
+        if "instance_graph_kernel" in kern:
+            t = kern["instance_graph_kernel"]["ms_per_launch"] * 1e-3
+            stages["graph_build"] = {"ms": t * 1e3, "GBps": alg["graph_build"]["bytes"] / t / 1e9,
+                                     "frac_hbm": alg["graph_build"]["bytes"] / t / 1e9 / hbm}
+        if "class_edges_kernel" in kern:
+            t = kern["class_edges_kernel"]["ms_per_launch"] * 1e-3
+            stages["atlas"] = {"ms": t * 1e3, "GBps": alg["atlas"]["bytes"] / t / 1e9,
+                               "frac_hbm": alg["atlas"]["bytes"] / t / 1e9 / hbm}
+        for name in ("discretize_exact_kernel", "discretize_tc_kernel"):
+            if name in kern:
+                t = kern[name]["ms_per_launch"] * 1e-3
+                stages["discretize"] = {"ms": t * 1e3, "TFLOPs": alg["discretize"]["flops"] / t / 1e12, "kernel": name}
+        # CPU baseline on a bounded sample (rank 0, N = 1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            Bs = c["B"]
+            cpu_head_time(c, vocab, sets, schema, gnn, 1, batch=Bs)
+            ips, med, cores, kind = cpu_head_time(c, vocab, sets, schema, gnn, 3, batch=Bs)
+            cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
+                   "sample": f"the full {Bs}-image cfg2 batch, K={c['K']} class side recomputed, 1 warm-up + median of 3 steps "
+                             f"({med:.2f} s/step); native loops: "
+                             f"{'reference C++ (oracle/_ref)' if kind == 'reference' else 'oracle C restatement'}"}
+        line = {"metric": "schema_head_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(c, world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "stages": stages, "kernels": kern,
+                "mean_vertices_per_image": n_bar}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,108 @@
+"""The fused, sync-free tensor path of the schema-inference head (what bench.py times and what the drop-in modules
+are built from):
+
+    mid_feat [1+L, bs, d], attention  ->  discretize  ->  instance graphs  ->  class atlas  ->  GNN x2  ->  logits
+
+Every stage is one or a few launches of libschemahead kernels on the current stream; nothing returns to the host
+(the list-returning module API needs one D2H copy of the graph sizes -- this path does not).  Reference call stack
+replaced: SchemaNetPredictor.forward (schema_inference/graph/__init__.py:37-57) below the backbone.
+"""
+from typing import Dict, Optional
+
+import torch
+
+from . import native
+
+
+class HeadWorkspace:
+    """Per-(batch, L) output buffers reused across steps (no allocation inside the timed region)."""
+
+    def __init__(self):
+        self.key = None
+        self.graphs: Optional[native.PackedGraphs] = None
+        self.ingredients = None
+
+    def get(self, bs, L, device):
+        key = (bs, L, str(device))
+        if key != self.key:
+            self.graphs = native.PackedGraphs(bs, L, device)
+            self.ingredients = torch.empty(bs, L, dtype=torch.int64, device=device)
+            self.key = key
+        return self.graphs, self.ingredients
+
+
+class SchemaHead:
+    """Functional head over a `SchemaNet` and a `Matcher` (the drop-in modules) and a codebook.
+
+    class_shard = (rank, world): this process embeds only its slice of the K class graphs and the [K, D] class
+    embeddings are all-gathered over NCCL (placement (i)); the batch is sharded by the caller.
+    """
+
+    def __init__(self, vocab: torch.Tensor, schema_net, matcher, class_shard=None, disc_mode=native.DISC_AUTO):
+        self.vocab = vocab
+        self.schema_net = schema_net
+        self.matcher = matcher
+        self.class_shard = class_shard
+        self.disc_mode = disc_mode
+        self.ws = HeadWorkspace()
+        self._class_cache = None
+
+    # -- stage 1 -------------------------------------------------------------------------------------------------
+    def discretize(self, mid_feat: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        T, bs, d = mid_feat.shape
+        L = T - 1
+        tokens = mid_feat[1:].reshape(L * bs, d)            # drop the cls token: a view, rows are token-major
+        native.discretize(tokens, self.vocab, out_idx=out, idx_rows=bs, idx_row_stride=L, idx_col_stride=1,
+                          mode=self.disc_mode)
+        return out
+
+    # -- stage 3, class side ---------------------------------------------------------------------------------------
+    def class_features(self) -> torch.Tensor:
+        sn, gnn = self.schema_net, self.matcher.gnn
+        vw, ew, ci = sn.vertex_weights.tensor, sn.edge_weights.tensor, sn.class_ingredients.tensor
+        K = vw.shape[0]
+        if self.class_shard is None:
+            cv, ce = native.class_atlas(vw, ew, sn.prune_node_threshold, True, sn.remove_self_loop)
+            return gnn(nodes=cv, edges=ce, ingredients=ci)
+        import torch.distributed as dist
+        rank, world = self.class_shard
+        per = (K + world - 1) // world
+        k0, k1 = min(rank * per, K), min((rank + 1) * per, K)
+        D = gnn.embed_dim
+        local = torch.zeros(per, D, dtype=torch.float32, device=vw.device)
+        if k1 > k0:
+            cv, ce = native.class_atlas(vw[k0:k1], ew[k0:k1], sn.prune_node_threshold, True, sn.remove_self_loop)
+            local[:k1 - k0] = gnn(nodes=cv, edges=ce, ingredients=ci[k0:k1])
+        full = torch.empty(world * per, D, dtype=torch.float32, device=vw.device)
+        dist.all_gather_into_tensor(full, local)              # the path's only collective: K*D*4 bytes over NVLink
+        return full[:K]
+
+    # -- whole head ----------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, mid_feat: torch.Tensor, attn: torch.Tensor = None, attn_cls: torch.Tensor = None,
+                extracted: torch.Tensor = None, cache_class: bool = False) -> Dict[str, torch.Tensor]:
+        """attn/attn_cls: raw head-averaged logits [bs, L, L] / [bs, L]; or `extracted` [bs*H, L+1, L+1] (the
+        backbone tap), in which case the head mean is fused into the graph-build read."""
+        sn = self.schema_net
+        T, bs, _ = mid_feat.shape
+        L = T - 1
+        graphs, ingredients = self.ws.get(bs, L, mid_feat.device)
+        self.discretize(mid_feat, ingredients)
+        geo = sn._geo(mid_feat.device)
+        heads = 0
+        if extracted is not None:
+            heads = extracted.shape[0] // bs
+            attn, attn_cls = extracted, None
+        native.instance_graphs(ingredients, attn, attn_cls, geo, sn.vertex_attribute_weights.tensor,
+                               sn.edge_attribute_weights.tensor, sn.clamp_vertex_attn, sn.clamp_edge_attn,
+                               raw_logits=True, heads=heads, mean=True, out=graphs)
+        if cache_class and self._class_cache is not None:
+            f_kg = self._class_cache
+        else:
+            f_kg = self.class_features()
+            self._class_cache = f_kg if cache_class else None
+        f_inst = self.matcher.gnn.forward_packed(graphs)
+        pred = native.similarity(f_inst, f_kg, self.matcher.similarity_name)
+        return {"pred": pred, "ingredients": ingredients, "graphs": graphs, "feat_instance": f_inst, "feat_class": f_kg}
+
+    __call__ = forward
