@@ -15,7 +15,7 @@ __device__ __forceinline__ float exact_distance(float xn, float cn, float dot)
 constexpr int kCandSlots = 16;   // near-tie candidates kept per row by the tensor-core path
 
 struct DiscWorkspace {
-    unsigned long long *counters;   // [0] rows re-checked, [1] rows whose candidate list overflowed
+    unsigned long long *counters;   // [0] rows re-checked, [1] rows whose candidate list overflowed, [2] max |c|^2 bits
     float *cn;                      // [M]  |c_j|^2
     float *xn;                      // [R]  |x_r|^2
     int *cand_count;                // [R]
@@ -31,7 +31,7 @@ inline DiscWorkspace carve_disc_workspace(void *base, int64_t R, int M)
     char *p = (char *)base;
     size_t off = 0;
     w.counters = (unsigned long long *)(p + off); off += 256;
-    w.cn = (float *)(p + off); off += ws_align(sizeof(float) * (size_t)M);
+    w.cn = (float *)(p + off); off += ws_align(sizeof(float) * ((size_t)M + 256));   // +inf padded to the N tile
     w.xn = (float *)(p + off); off += ws_align(sizeof(float) * (size_t)R);
     w.cand_count = (int *)(p + off); off += ws_align(sizeof(int) * (size_t)R);
     w.cand_idx = (int *)(p + off); off += ws_align(sizeof(int) * (size_t)R * kCandSlots);
@@ -40,6 +40,8 @@ inline DiscWorkspace carve_disc_workspace(void *base, int64_t R, int M)
 }
 
 int launch_row_sqnorm(const float *x, int64_t rows, int d, float *out, cudaStream_t st);
+// |c_j|^2 into ws.cn (+inf padding up to a multiple of 256) and max_j |c_j|^2 into ws.counters[2]
+int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws, cudaStream_t st);
 int launch_gather(const float *vocab, const int64_t *idx, int64_t idx_rows, int64_t idx_row_stride,
                   int64_t idx_col_stride, int64_t R, int d, float *out, cudaStream_t st);
 int launch_discretize_exact(const float *X, const float *C, const float *cn, int64_t R, int d, int M, int64_t *out_idx,

@@ -1,19 +1,322 @@
-// discretize_tc.cu -- stage 1 on tcgen05 tensor cores (placeholder until the TMA/tcgen05 kernel lands).
+// discretize_tc.cu -- stage 1 on the 5th-generation tensor cores: TMA-fed tcgen05 (kind::tf32) GEMM with the
+// distance + argmin fused into the TMEM epilogue, and an exact fp32 re-check of near ties.
+//
+// Replaces `torch.cdist(seq, vocabulary.weight).argmin(dim=1)` (discretization/discretization.py:65).
+//
+//   scores  s[r, j] = |c_j|^2 - 2 x_r.c_j            (|x_r|^2 is constant per row: irrelevant for the argmin)
+//   coarse  x_r.c_j from tcgen05.mma kind::tf32: fp32 tiles go from HBM to swizzled shared memory by TMA and are fed
+//           to the tensor core as they are (it uses the top 19 bits), fp32 accumulation in tensor memory
+//   epilogue one thread per token row (TMEM lane): running minimum over all N tiles + the list of every codeword
+//           whose coarse score is within `band` of it (band = beta * 2^-10 * |x_r| * max_j |c_j|)
+//   recheck rows with more than one candidate are re-scored in exact fp32 with the reference formula
+//           sqrt(max(|x|^2 + |c|^2 - 2 x.c, 0)), lowest index on ties (the clamp and the sqrt create ties)
+//
+// Warp roles (192 threads, one CTA per SM, persistent over 128-row blocks):
+//   warp 0: TMA producer      warp 1: TMEM allocator + MMA issuer (one elected lane)      warps 2-5: epilogue
+// Pipelines: a 4-stage shared-memory ring (full/empty mbarriers, slots freed by tcgen05.commit) and a 2-stage TMEM
+// accumulator ring (tmem_full/tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "discretize.cuh"
+#include "tc_common.cuh"
 
 namespace sh {
 
-bool discretize_tc_supported(int64_t R, int d, int M)
+using namespace tc;
+
+constexpr int TC_BM = 128;       // token rows per tile (UMMA M)
+constexpr int TC_BK = 32;        // fp32 per k-block = one 128-byte swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int kOverflowMark = -1;
+
+struct DiscTcArgs {
+    int64_t R;
+    int d, M;
+    int num_m_blocks, num_n_blocks, num_k_blocks;
+    const float *cn;       // [M padded to the N tile] |c_j|^2, +inf beyond M
+    const float *xn;       // [R]
+    const unsigned *cmax_bits;   // bit pattern of max_j |c_j|^2
+    float beta;
+    int64_t *out_idx;
+    int64_t idx_rows, idx_row_stride, idx_col_stride;
+    int *cand_count;       // [R]
+    int *cand_idx;         // [R, kCandSlots]
+};
+
+template <int BN>
+struct DiscTcSmem {
+    static constexpr int kABytes = TC_BM * TC_BK * 4;
+    static constexpr int kBBytes = BN * TC_BK * 4;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = TC_STAGES * kStageBytes;
+    static constexpr int kCandOffset = kBarOffset + 256;
+    static constexpr int kTotal = kCandOffset + TC_BM * kCandSlots * 8 + 1024;   // + slack for 1024-B alignment
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DiscTcArgs a)
 {
-    (void)R; (void)d; (void)M;
-    return false;
+    using S = DiscTcSmem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + S::kBarOffset);
+    uint64_t *empty = full + TC_STAGES;
+    uint64_t *tmem_full = empty + TC_STAGES;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 2);
+    float *cand_s = (float *)(smem + S::kCandOffset);
+    int *cand_i = (int *)(cand_s + TC_BM * kCandSlots);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mb = blockIdx.x; mb < a.num_m_blocks; mb += gridDim.x)
+                for (int nb = 0; nb < a.num_n_blocks; ++nb)
+                    for (int kb = 0; kb < a.num_k_blocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t *sa = smem + stage * S::kStageBytes;
+                        mbar_arrive_expect_tx(&full[stage], S::kStageBytes);
+                        tma_load_2d(sa, &tmA, &full[stage], kb * TC_BK, mb * TC_BM);
+                        tma_load_2d(sa + S::kABytes, &tmB, &full[stage], kb * TC_BK, nb * BN);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+        int stage = 0, as = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int mb = blockIdx.x; mb < a.num_m_blocks; mb += gridDim.x)
+            for (int nb = 0; nb < a.num_n_blocks; ++nb) {
+                mbar_wait(&tmem_empty[as], aphase ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < a.num_k_blocks; ++kb) {
+                    mbar_wait(&full[stage], phase);          // TMA bytes have landed
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+                        const uint64_t da = make_desc_k_sw128(sa), db = make_desc_k_sw128(sa + S::kABytes);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k)   // UMMA K = 8 for tf32 = 32 bytes along the swizzle row
+                            umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        umma_commit(&empty[stage]);          // slot is free once these MMAs have read it
+                        if (kb == a.num_k_blocks - 1) umma_commit(&tmem_full[as]);
+                    }
+                    __syncwarp();
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+    } else {
+        // ===================== epilogue: fused score + running argmin + near-tie candidates =====================
+        const int wq = warp & 3;                       // TMEM lane quarter this warp may access
+        const int row_in_tile = wq * 32 + lane;
+        float *my_s = cand_s + row_in_tile * kCandSlots;
+        int *my_i = cand_i + row_in_tile * kCandSlots;
+        const float cmax = sqrtf(__uint_as_float(*a.cmax_bits));
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int mb = blockIdx.x; mb < a.num_m_blocks; mb += gridDim.x) {
+            const int64_t row = (int64_t)mb * TC_BM + row_in_tile;
+            const bool valid = row < a.R;
+            const float band = valid ? a.beta * 9.765625e-4f * sqrtf(a.xn[row]) * cmax : 0.0f;
+            float m_run = INFINITY;
+            int cnt = 0;
+            bool overflow = false;
+            for (int nb = 0; nb < a.num_n_blocks; ++nb) {
+                mbar_wait(&tmem_full[as], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int n_base = nb * BN + c * 32;
+                    if (n_base >= a.M) break;
+                    float v[32];
+                    tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+                    const float4 *cn4 = reinterpret_cast<const float4 *>(a.cn + n_base);
+                    float cmin = INFINITY;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 cc = __ldg(cn4 + q);      // +inf beyond M: out-of-range columns never win
+                        v[4 * q + 0] = fmaf(-2.0f, v[4 * q + 0], cc.x);
+                        v[4 * q + 1] = fmaf(-2.0f, v[4 * q + 1], cc.y);
+                        v[4 * q + 2] = fmaf(-2.0f, v[4 * q + 2], cc.z);
+                        v[4 * q + 3] = fmaf(-2.0f, v[4 * q + 3], cc.w);
+                        cmin = fminf(cmin, fminf(fminf(v[4 * q], v[4 * q + 1]), fminf(v[4 * q + 2], v[4 * q + 3])));
+                    }
+                    if (cmin <= m_run + band) {
+                        m_run = fminf(m_run, cmin);
+                        const float thr = m_run + band;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (v[j] <= thr && !overflow) {
+                                if (cnt == kCandSlots) {       // compact: drop entries the new minimum has ruled out
+                                    int keep = 0;
+                                    for (int t = 0; t < kCandSlots; ++t)
+                                        if (my_s[t] <= thr) { my_s[keep] = my_s[t]; my_i[keep] = my_i[t]; ++keep; }
+                                    cnt = keep;
+                                }
+                                if (cnt < kCandSlots) { my_s[cnt] = v[j]; my_i[cnt] = n_base + j; ++cnt; }
+                                else overflow = true;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (valid) {
+                const float thr = m_run + band;
+                int keep = 0, first = 0;
+                if (!overflow)
+                    for (int t = 0; t < cnt; ++t)
+                        if (my_s[t] <= thr) { if (keep == 0) first = my_i[t]; a.cand_idx[row * kCandSlots + keep] = my_i[t]; ++keep; }
+                if (overflow) a.cand_count[row] = kOverflowMark;
+                else {
+                    a.cand_count[row] = keep;
+                    if (keep == 1)
+                        a.out_idx[(row % a.idx_rows) * a.idx_row_stride + (row / a.idx_rows) * a.idx_col_stride] = first;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-int launch_discretize_tc(const float *, const float *, int64_t, int, int, int64_t *, int64_t, int64_t, int64_t,
-                         const DiscWorkspace &, cudaStream_t)
+// Exact fp32 re-check of the rows the tensor-core pass could not decide (one warp per row).
+__global__ void __launch_bounds__(256)
+discretize_recheck_kernel(const float *__restrict__ X, const float *__restrict__ C, const float *__restrict__ cn,
+                          const float *__restrict__ xn, int64_t R, int d, int M, const int *__restrict__ cand_count,
+                          const int *__restrict__ cand_idx, int64_t *__restrict__ out_idx, int64_t idx_rows,
+                          int64_t idx_row_stride, int64_t idx_col_stride, unsigned long long *counters)
 {
-    set_error("discretize: tensor-core path not built");
-    return 1;
+    const int lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < R; row += (int64_t)gridDim.x * 8) {
+        const int cnt = cand_count[row];
+        if (cnt == 1) continue;
+        const float *x = X + row * d;
+        const float xr = xn[row];
+        float best_d = INFINITY;
+        int best_i = 0x7fffffff;
+        const bool full_scan = (cnt == kOverflowMark || cnt <= 0);
+        const int total = full_scan ? M : cnt;
+        for (int t = 0; t < total; ++t) {
+            const int n = full_scan ? t : cand_idx[row * kCandSlots + t];
+            const float *c = C + (size_t)n * d;
+            float dot = 0.0f;
+            for (int k = lane; k < d; k += kWarp) dot = fmaf(x[k], c[k], dot);
+            dot = warp_sum(dot);
+            const float dist = exact_distance(xr, cn[n], dot);
+            if (dist < best_d || (dist == best_d && n < best_i)) { best_d = dist; best_i = n; }
+        }
+        if (lane == 0) {
+            if (best_i == 0x7fffffff) best_i = 0;
+            out_idx[(row % idx_rows) * idx_row_stride + (row / idx_rows) * idx_col_stride] = best_i;
+            atomicAdd(&counters[0], 1ULL);
+            if (full_scan) atomicAdd(&counters[1], 1ULL);
+        }
+    }
+}
+
+// |c_j|^2 (+inf padding up to `padded`) and the bit pattern of max_j |c_j|^2
+__global__ void __launch_bounds__(256)
+codebook_norms_kernel(const float *__restrict__ C, int M, int padded, int d, float *__restrict__ cn, unsigned *cmax_bits)
+{
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < padded; r += gridDim.x * 8) {
+        if (r >= M) { if (lane == 0) cn[r] = INFINITY; continue; }
+        const float *p = C + (size_t)r * d;
+        float s = 0.0f;
+        for (int k = lane; k < d; k += kWarp) s = fmaf(p[k], p[k], s);
+        s = warp_sum(s);
+        if (lane == 0) { cn[r] = s; atomicMax(cmax_bits, __float_as_uint(s)); }
+    }
+}
+
+bool discretize_tc_supported(int64_t R, int d, int M)
+{
+    // TMA needs 16-byte aligned row strides; tiny problems are not worth a tensor-core launch
+    return d % 4 == 0 && d >= 32 && M >= 16 && R >= 1 && encode_tiled_fn() != nullptr;
+}
+
+int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws, cudaStream_t st)
+{
+    const int padded = (M + 255) / 256 * 256;
+    SH_LAUNCH("codebook_norms_kernel", st,
+              codebook_norms_kernel<<<ceil_div(padded, 8), 256, 0, st>>>(C, M, padded, d, ws.cn, (unsigned *)(ws.counters + 2)));
+    SH_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int BN>
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const DiscTcArgs &a, cudaStream_t st)
+{
+    using S = DiscTcSmem<BN>;
+    static bool configured = false;
+    if (!configured) {
+        SH_CHECK_CUDA(cudaFuncSetAttribute(discretize_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        configured = true;
+    }
+    const int grid = min(a.num_m_blocks, sm_count());
+    SH_LAUNCH("discretize_tc_kernel", st, discretize_tc_kernel<BN><<<grid, TC_THREADS, S::kTotal, st>>>(tmA, tmB, a));
+    SH_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M, int64_t *out_idx, int64_t idx_rows,
+                         int64_t idx_row_stride, int64_t idx_col_stride, const DiscWorkspace &ws, cudaStream_t st)
+{
+    SH_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)C % 16 == 0), "discretize: tensor-core path needs 16-byte aligned inputs");
+    const int BN = M > 128 ? 256 : (M > 64 ? 128 : 64);
+    CUtensorMap tmA, tmB;
+    if (make_tmap_f32(&tmA, X, (uint64_t)d, (uint64_t)R, 1, (uint64_t)d, 0, TC_BM)) return 1;
+    if (make_tmap_f32(&tmB, C, (uint64_t)d, (uint64_t)M, 1, (uint64_t)d, 0, (uint32_t)BN)) return 1;
+    if (launch_row_sqnorm(X, R, d, ws.xn, st)) return 1;
+    DiscTcArgs a{};
+    a.R = R; a.d = d; a.M = M;
+    a.num_m_blocks = (int)ceil_div64(R, TC_BM);
+    a.num_n_blocks = ceil_div(M, BN);
+    a.num_k_blocks = ceil_div(d, TC_BK);
+    a.cn = ws.cn; a.xn = ws.xn; a.cmax_bits = (const unsigned *)(ws.counters + 2);
+    // band = beta * 2^-10 * |x| * max|c|: >= 13 sigma of the tf32 truncation noise for i.i.d. data, and the rigorous
+    // worst-case bound when beta reaches 8 ("tf32 band")
+    float beta = 16.0f / sqrtf((float)d);
+    a.beta = beta < 1.0f ? 1.0f : (beta > 8.0f ? 8.0f : beta);
+    a.out_idx = out_idx; a.idx_rows = idx_rows; a.idx_row_stride = idx_row_stride; a.idx_col_stride = idx_col_stride;
+    a.cand_count = ws.cand_count; a.cand_idx = ws.cand_idx;
+    int rc;
+    if (BN == 256) rc = launch_tc<256>(tmA, tmB, a, st);
+    else if (BN == 128) rc = launch_tc<128>(tmA, tmB, a, st);
+    else rc = launch_tc<64>(tmA, tmB, a, st);
+    if (rc) return rc;
+    const int grid = (int)min(ceil_div64(R, 8), (int64_t)sm_count() * 8);
+    SH_LAUNCH("discretize_recheck_kernel", st,
+              discretize_recheck_kernel<<<grid, 256, 0, st>>>(X, C, ws.cn, ws.xn, R, d, M, ws.cand_count, ws.cand_idx, out_idx,
+                                                              idx_rows, idx_row_stride, idx_col_stride, ws.counters));
+    SH_CHECK_LAUNCH();
+    return 0;
 }
 
 }  // namespace sh

@@ -1,0 +1,182 @@
+// tc_common.cuh -- hand-written sm_100a building blocks: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (UMMA) and
+// tensor-memory (TMEM) wrappers in inline PTX, plus the host-side tensor-map encoder.  Bit layouts follow the PTX
+// ISA "tcgen05" chapter (shared-memory matrix descriptor, instruction descriptor); no CUTLASS code is used.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace sh {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (sticky error the host sees), never hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {   // ~2 s at 1.9 GHz
+            printf("libschemahead: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA tiled loads (global -> swizzled shared memory), completion on an mbarrier
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (UMMA / TMA reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// tcgen05: TMEM allocation, MMA issue, commit, TMEM loads
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)   // whole warp
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)     // whole warp
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32 (fp32 containers, 10-bit mantissa used), one elected thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+// all previously issued MMAs of this thread -> arrive on the mbarrier when they have completed
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets row (lane base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (what a TMA box of 32 fp32 x rows with
+// CU_TENSOR_MAP_SWIZZLE_128B produces): 8-row groups of 1024 B (stride byte offset), version 1 (sm_100).
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4   [46,48) version = 1   [61,64) layout type: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+// Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major.
+//   [4,6) C format: 1 = F32   [7,10) A format: 2 = TF32   [10,13) B format: 2 = TF32
+//   [15] A major, [16] B major: 0 = K   [17,23) N >> 3   [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: tensor maps (cuTensorMapEncodeTiled fetched through the runtime, no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// fp32 row-major [batch, rows, cols] (cols contiguous, row stride ld floats, batch stride in floats); the box is
+// {32 floats (128 B, one swizzle row), box_rows, 1}; out-of-bounds elements are zero-filled.
+inline int make_tmap_f32(CUtensorMap *map, const float *base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld,
+                         uint64_t batch_stride, uint32_t box_rows)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return 1; }
+    cuuint64_t dims[3] = {cols, rows, batch};
+    cuuint64_t strides[2] = {ld * sizeof(float), batch_stride * sizeof(float)};
+    cuuint32_t box[3] = {32, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t rank = batch > 1 ? 3 : 2;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return 1; }
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace sh

@@ -168,6 +168,8 @@ def discretize(tokens, vocab, out_idx=None, idx_rows=None, idx_row_stride=1, idx
     M = vocab.shape[0]
     if vocab.shape[1] != d:
         raise RuntimeError(f"dimension {d} not match to {vocab.shape[1]}")
+    if mode == DISC_AUTO and os.environ.get("SCHEMANET_DISC_MODE", "") == "exact":
+        mode = DISC_EXACT          # debugging aid: force the fp32 CUDA-core scan
     if out_idx is None:
         out_idx = torch.empty(R, dtype=torch.int64, device=tokens.device)
     if idx_rows is None:

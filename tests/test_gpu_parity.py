@@ -198,6 +198,28 @@ def test_discretize_vs_oracle(B, d, M, mode):
         assert len(bad) == 0
 
 
+@pytest.mark.parametrize("B,d,M,mode", [(64, 384, 1024, "hard"), (16, 768, 8000, "hard"), (64, 192, 128, "easy"),
+                                        (7, 96, 200, "hard")])
+def test_discretize_tensor_core_vs_exact_path(B, d, M, mode):
+    """tcgen05 (tf32 coarse pass + fp32 re-check) against the fp32 CUDA-core scan on the same device: any
+    difference must sit on an fp32-ambiguous row; the re-check statistics are reported."""
+    from schemanet_b200 import native
+    vocab, mid, _, _ = ho.synth_inputs(B, d, M, seed=2000 + M, mode=mode)
+    flat = mid[1:].reshape(-1, d).cuda()
+    v = vocab.cuda()
+    exact = native.discretize(flat, v, mode=native.DISC_EXACT)
+    tens, ws = native.discretize(flat, v, mode=native.DISC_TENSOR, return_workspace=True)
+    stats = native.discretize_stats(ws)
+    bad = (exact != tens).nonzero().flatten().cpu()
+    print(f"tensor-core discretize B={B} d={d} M={M} {mode}: recheck rows {stats['recheck_rows']} / {flat.shape[0]}, "
+          f"overflow rows {stats['overflow_rows']}, mismatches vs exact {len(bad)}")
+    if len(bad):
+        _, gap = ho.discretize_fp64_gap(flat.cpu()[bad], vocab)
+        assert bool((gap < 1e-6).all()), f"{len(bad)} mismatches on unambiguous rows (largest gap {gap.max():.2e})"
+    assert len(bad) <= max(1, flat.shape[0] // 2000)
+    assert stats["overflow_rows"] <= flat.shape[0] // 100
+
+
 def test_discretize_edge_cases():
     from schemanet_b200 import native
     g = torch.Generator().manual_seed(5)
