@@ -270,7 +270,7 @@ def run_gpu_arm(args):
             kern[k]["share"] = kern[k]["ms_total"] / total_prof if total_prof else None
         dom = max(prof.items(), key=lambda kv: kv[1][1])[0]
         roof = None
-        if dom == "gnn_adj_gemm":
+        if dom in ("gnn_adj_gemm", "gnn_adj_gemm_tc"):
             # launches alternate class side (K graphs of Vc nodes) and instance side; the class-side launches dominate.
             # achieved = algorithmic flops of ALL adjacency-GEMM launches in a step / their summed duration
             per_step_flops = 2 * alg["class_adj_gemm"]["flops"] + c["B"] * 2 * 2.0 * n_bar * n_bar * c["D"]
@@ -278,7 +278,8 @@ def run_gpu_arm(args):
             peak = peaks["bf16_tflops_sustained"] / 2     # TF32 tensor peak ~ half the measured BF16 peak
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": None, "peak_source": peaks["source"] + " bf16 sustained / 2 (TF32-equivalent)",
-                    "note": "fp32 CUDA-core FMA path this round; see DESIGN.md for the tcgen05 3xTF32 plan"}
+                    "note": ("3xTF32 on tcgen05: achieved counts the algorithmic fp32 flops once (the tensor cores "
+                             "execute 3x that)" if dom.endswith("_tc") else "fp32 CUDA-core FMA path")}
         else:
             key = {"discretize_exact_kernel": "discretize", "instance_graph_kernel": "graph_build",
                    "class_edges_kernel": "atlas"}.get(dom)

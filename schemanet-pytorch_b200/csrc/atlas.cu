@@ -63,7 +63,10 @@ class_edges_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, 
                         const float4 m = *reinterpret_cast<const float4 *>(cvk + j);
                         const bool k0 = keep_i && m.x > thr, k1 = keep_i && m.y > thr, k2 = keep_i && m.z > thr,
                                    k3 = keep_i && m.w > thr;
-                        if (prune_in_place && !(k0 && k1 && k2 && k3)) {
+                        // in-place prune of the parameter (schema_net.py:164); entries that are already zero (every
+                        // call after the first) are not rewritten -- same memory image, half the HBM writes
+                        const bool dirty = (!k0 && x.x != 0.f) || (!k1 && x.y != 0.f) || (!k2 && x.z != 0.f) || (!k3 && x.w != 0.f);
+                        if (prune_in_place && dirty) {
                             float4 z = make_float4(k0 ? x.x : 0.f, k1 ? x.y : 0.f, k2 ? x.z : 0.f, k3 ? x.w : 0.f);
                             *reinterpret_cast<float4 *>(src + j) = z;
                         }
@@ -93,7 +96,7 @@ class_edges_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, 
                 float x = src[j];
                 if (prune) {
                     const bool keep = keep_i && cvk[j] > thr;
-                    if (!keep) { if (prune_in_place) src[j] = 0.f; x = 0.f; }
+                    if (!keep) { if (prune_in_place && x != 0.f) src[j] = 0.f; x = 0.f; }
                 }
                 acc += fmaxf(x, 0.f);
             }

@@ -13,6 +13,8 @@
 //     last layer's LN pass also produces the vertex-weighted pooling partials, reduced without atomics.
 // All products accumulate in fp32 FMA (the north star's 1e-5 logit tolerance rules out plain TF32 here).
 #include "common.cuh"
+#include <stdlib.h>
+#include "gnn_tc.cuh"
 
 namespace sh {
 
@@ -243,7 +245,8 @@ extern "C" size_t sh_gnn_workspace_bytes(int G, int n_max, int D)
     const size_t slab = align_up((size_t)G * n_max * D * sizeof(float), 256);
     const size_t part = align_up((size_t)G * pool_chunks(n_max) * D * sizeof(float), 256);
     const size_t pooled = align_up((size_t)G * D * sizeof(float), 256);
-    return 2 * slab + part + pooled;
+    const size_t tc = gnn_tc_supported(D, n_max) ? gnn_tc_workspace_bytes(G, n_max, D, pool_chunks(n_max)) : 0;
+    return 2 * slab + part + pooled + tc;
 }
 
 extern "C" int sh_dev_gnn_forward(const sh_gnn_params *p, int G, int n_fixed, const int32_t *sizes, const int64_t *ids,
@@ -264,7 +267,13 @@ extern "C" int sh_dev_gnn_forward(const sh_gnn_params *p, int G, int n_fixed, co
     float *partial = (float *)(ws + 2 * slab);
     float *pooled = (float *)(ws + 2 * slab + align_up((size_t)G * chunks * D * sizeof(float), 256));
 
-    for (int l = 0; l < p->num_layers; ++l) {
+    const bool tensor_path = gnn_tc_supported(D, n_fixed) && getenv("SCHEMANET_GNN_SIMT") == nullptr;
+    if (tensor_path) {
+        char *tc_ws = ws + 2 * slab + align_up((size_t)G * chunks * D * sizeof(float), 256) + align_up((size_t)G * D * sizeof(float), 256);
+        if (gnn_forward_tc(p, G, n_fixed, sizes, ids, vertex_w, ld_v, edges, edge_batch_stride, edge_ld, chunks, partial,
+                           tc_ws, st)) return 1;
+    }
+    for (int l = 0; l < p->num_layers && !tensor_path; ++l) {
         // Y = ((E + E^T)/2 + I) X          (gnn.py:27-30); layer 0 gathers X from the embedding table (:91)
         GemmArgs a{};
         a.A = edges; a.a_batch = edge_batch_stride; a.lda = edge_ld;

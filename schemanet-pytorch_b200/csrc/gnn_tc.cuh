@@ -1,0 +1,14 @@
+// gnn_tc.cuh -- tensor-core (tcgen05, 3xTF32) GNN layer path, see gnn_tc.cu
+#pragma once
+#include "common.cuh"
+
+namespace sh {
+
+bool gnn_tc_supported(int D, int n_fixed);
+size_t gnn_tc_workspace_bytes(int G, int n_fixed, int D, int chunks);
+// Runs all GNN layers on the tensor cores and leaves the vertex-weighted pooling partials [G, chunks, D] in `partial`.
+int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *sizes, const int64_t *ids,
+                   const float *vertex_w, int ld_v, const float *edges, int64_t edge_batch_stride, int edge_ld, int chunks,
+                   float *partial, void *workspace, cudaStream_t st);
+
+}  // namespace sh

@@ -320,6 +320,35 @@ def test_class_side_large_tile_path():
     rel_close(got, ho.gnn_forward(params, nodes, edges, ids, None), what="gnn class side")
 
 
+@pytest.mark.parametrize("K,Vc,masked", [(3, 300, False), (5, 1024, False), (9, 196, True), (2, 33, True)])
+def test_gnn_tensor_core_path_vs_oracle(K, Vc, masked):
+    """embed_dim 256 takes the tcgen05 3xTF32 path (adjacency prep, TMA-fed UMMA, LayerNorm fused in the TMEM
+    epilogue); it must meet the same 1e-5 bar against the fp32 oracle as the CUDA-core path."""
+    from schema_inference.graph import Matcher
+    gen = torch.Generator().manual_seed(80 + Vc)
+    M, D = 1500, 256
+    params = ho.synth_gnn(M, D, seed=81)
+    params["layers.0.norm.weight"] = torch.rand(D, generator=gen) + 0.5
+    params["layers.1.norm.bias"] = torch.randn(D, generator=gen) * 0.1
+    m = Matcher("inner_product", M, dict(embed_dim=D, num_layers=2)).cuda()
+    m.gnn.load_state_dict(params)
+    nodes = torch.rand(K, Vc, generator=gen) / Vc
+    edges = torch.rand(K, Vc, Vc, generator=gen) / Vc
+    ids = torch.stack([torch.randperm(M, generator=gen)[:Vc] for _ in range(K)])
+    mask = None
+    if masked:
+        sizes = torch.randint(1, Vc + 1, (K,), generator=gen)
+        sizes[0] = Vc
+        mask = torch.arange(Vc)[None, :] >= sizes[:, None]
+        nodes[mask] = 0
+        ids[mask] = M
+        edges = edges * (~mask)[:, :, None] * (~mask)[:, None, :]
+    want = ho.gnn_forward(params, nodes, edges, ids, mask)
+    with torch.no_grad():
+        got = m.gnn(nodes.cuda(), edges.cuda(), ids.cuda(), mask.cuda() if masked else None)
+    rel_close(got, want, what="gnn tensor-core path")
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE configs[1]: B=256, d=384, M=1024) -- no oracle needed
 # ----------------------------------------------------------------------------------------------------------------
