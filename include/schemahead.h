@@ -176,6 +176,21 @@ int sh_dev_gnn_forward(const sh_gnn_params *params, int G, int n_fixed, const in
                        const int32_t *mean_div, float *out, void *workspace, size_t workspace_bytes,
                        sh_stream_t stream);
 
+/* Stage 3a + class side of stage 3b in one call (what SchemaNetPredictor.forward does with get_atlas() followed by the
+ * second self.gnn(...) of Matcher.forward, schema_net.py:177-184 + match.py:66-70): writes class_vertices [K,Vc],
+ * class_edges [K,Vc,Vc] and the class embeddings feat_class [K,D].  The tensor-core path compacts every class graph to
+ * its un-pruned vertices first (pruned vertices have all-zero edge rows/columns, so the result is unchanged). */
+size_t sh_class_side_workspace_bytes(int K, int Vc, int D);
+/* GNN.forward on the class graphs get_atlas() produced (match.py:66-70), given the prune threshold they were built with
+ * (< 0: none): same result as sh_dev_gnn_forward, pruned vertices are skipped.  Workspace: sh_class_side_workspace_bytes. */
+int sh_dev_gnn_forward_class(const sh_gnn_params *params, int K, int Vc, const float *class_vertices,
+                             const float *class_edges, const int64_t *class_ingredients, float prune_threshold,
+                             float *feat_class, void *workspace, size_t workspace_bytes, sh_stream_t stream);
+int sh_dev_class_side(const sh_gnn_params *params, const float *vertex_weights, float *edge_weights,
+                      const int64_t *class_ingredients, int K, int Vc, float prune_threshold, int prune_in_place,
+                      int remove_self_loop, float *class_vertices, float *class_edges, float *feat_class,
+                      void *workspace, size_t workspace_bytes, sh_stream_t stream);
+
 #define SH_SIM_INNER_PRODUCT 0
 #define SH_SIM_COSINE 1
 #define SH_SIM_EUCLIDEAN 2

@@ -78,12 +78,15 @@ class_edges_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, 
                 }
             }
             acc = warp_sum(acc);
+            // one reciprocal per row: pruned entries are exact zeros and 0 / acc would take the IEEE-division slow path
+            // for most of the tensor; x * (1 / acc) differs from x / acc by at most 1 ulp and keeps 0 * inf = NaN -> 0
+            const float inv = 1.0f / acc;
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 const int j = (c * kWarp + lane) * 4;
                 if (j < Vc) {
-                    float4 o = make_float4(nan_to_num0(v[c].x / acc), nan_to_num0(v[c].y / acc),
-                                           nan_to_num0(v[c].z / acc), nan_to_num0(v[c].w / acc));
+                    float4 o = make_float4(nan_to_num0(v[c].x * inv), nan_to_num0(v[c].y * inv),
+                                           nan_to_num0(v[c].z * inv), nan_to_num0(v[c].w * inv));
                     if (remove_self_loop && i >= j && i < j + 4) {
                         if (i == j) o.x = 0.f; else if (i == j + 1) o.y = 0.f; else if (i == j + 2) o.z = 0.f; else o.w = 0.f;
                     }
@@ -101,10 +104,11 @@ class_edges_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, 
                 acc += fmaxf(x, 0.f);
             }
             acc = warp_sum(acc);
+            const float inv = 1.0f / acc;
             for (int j = lane; j < Vc; j += kWarp) {
                 float x = src[j];   // pruned entries were just zeroed in place or are re-masked here
                 if (prune && !(keep_i && cvk[j] > thr)) x = 0.f;
-                float o = nan_to_num0(fmaxf(x, 0.f) / acc);
+                float o = nan_to_num0(fmaxf(x, 0.f) * inv);
                 if (remove_self_loop && i == j) o = 0.f;
                 dst[j] = o;
             }

@@ -233,9 +233,44 @@ similarity_kernel(const float *__restrict__ fi, const float *__restrict__ fk, in
     }
 }
 
+// pooled[g] = (sum of the chunk partials) / N  (mean over the PADDED node count, gnn.py:96), then out = fc(pooled)
+// (gnn.py:97).  One CTA per graph: the pooled vector lives in shared memory, one warp per output feature reads a
+// contiguous row of fc_w.
+__global__ void __launch_bounds__(256)
+pool_fc_kernel(const float *__restrict__ partial, int chunks, int D, int n_fixed, const int32_t *__restrict__ mean_div,
+               const float *__restrict__ fc_w, const float *__restrict__ fc_b, float *__restrict__ out)
+{
+    extern __shared__ float pooled[];
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float div = (float)(mean_div ? *mean_div : n_fixed);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float t = 0.0f;
+        for (int c = 0; c < chunks; ++c) t += partial[((size_t)g * chunks + c) * D + d];
+        pooled[d] = t / div;
+    }
+    __syncthreads();
+    for (int o = warp; o < D; o += (int)(blockDim.x >> 5)) {
+        const float *w = fc_w + (size_t)o * D;
+        float acc = 0.0f;
+        for (int d = lane; d < D; d += kWarp) acc = fmaf(pooled[d], w[d], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) out[(size_t)g * D + o] = acc + fc_b[o];
+    }
+}
+
 }  // namespace sh
 
 using namespace sh;
+
+static int launch_pool_fc(const sh_gnn_params *p, const float *partial, int G, int chunks, int n_fixed,
+                          const int32_t *mean_div, float *out, cudaStream_t st)
+{
+    const int D = p->embed_dim;
+    SH_LAUNCH("gnn_pool_fc", st,
+              pool_fc_kernel<<<G, 256, (size_t)D * sizeof(float), st>>>(partial, chunks, D, n_fixed, mean_div, p->fc_w, p->fc_b, out));
+    SH_CHECK_LAUNCH();
+    return 0;
+}
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static int pool_chunks(int n_max) { return n_max >= 512 ? 8 : (n_max >= 128 ? 4 : 1); }
@@ -303,16 +338,49 @@ extern "C" int sh_dev_gnn_forward(const sh_gnn_params *p, int G, int n_fixed, co
         }
         SH_CHECK_LAUNCH();
     }
-    SH_LAUNCH("pool_finish_kernel", st, pool_finish_kernel<<<G, 256, 0, st>>>(partial, G, chunks, D, n_fixed, mean_div, pooled));
-    SH_CHECK_LAUNCH();
-    // out = pooled fc_w^T + fc_b              (gnn.py:97)
-    GemmArgs f{};
-    f.A = pooled; f.a_batch = 0; f.lda = D;
-    f.B = p->fc_w; f.b_batch = 0; f.ldb = D; f.bias = p->fc_b;
-    f.C = out; f.c_batch = 0; f.ldc = D;
-    f.M = G; f.K = D; f.N = D; f.G = 1;
-    if (launch_sgemm<A_ROWMAJOR, B_TRANSPOSED>(f, st, "gnn_fc_gemm")) return 1;
-    return 0;
+    return launch_pool_fc(p, partial, G, chunks, n_fixed, mean_div, out, st);
+}
+
+extern "C" size_t sh_class_side_workspace_bytes(int K, int Vc, int D) { return sh_gnn_workspace_bytes(K, Vc, D); }
+
+// Stage 3a + the class side of stage 3b in one call: class_vertices / class_edges (the tensors get_atlas() returns) and
+// the [K, D] class embeddings.  On the tensor-core path the class graphs are compacted to their un-pruned vertices.
+extern "C" int sh_dev_class_side(const sh_gnn_params *p, const float *vertex_weights, float *edge_weights,
+                                 const int64_t *class_ingredients, int K, int Vc, float prune_threshold,
+                                 int prune_in_place, int remove_self_loop, float *class_vertices, float *class_edges,
+                                 float *feat_class, void *workspace, size_t workspace_bytes, sh_stream_t stream)
+{
+    SH_REQUIRE(p && K > 0 && Vc > 0 && class_vertices && class_edges && feat_class, "class_side: bad arguments");
+    const int D = p->embed_dim;
+    SH_REQUIRE(workspace_bytes >= sh_class_side_workspace_bytes(K, Vc, D), "class_side: workspace too small");
+    if (sh_dev_class_atlas(vertex_weights, edge_weights, K, Vc, prune_threshold, prune_in_place, remove_self_loop,
+                           class_vertices, class_edges, stream)) return 1;
+    return sh_dev_gnn_forward_class(p, K, Vc, class_vertices, class_edges, class_ingredients, prune_threshold, feat_class,
+                                    workspace, workspace_bytes, stream);
+}
+
+// GNN.forward on the K class graphs produced by get_atlas(): like sh_dev_gnn_forward, but knows that vertices with
+// class_vertices <= prune_threshold have all-zero edge rows/columns and compacts them away on the tensor-core path.
+extern "C" int sh_dev_gnn_forward_class(const sh_gnn_params *p, int K, int Vc, const float *class_vertices,
+                                        const float *class_edges, const int64_t *class_ingredients, float prune_threshold,
+                                        float *feat_class, void *workspace, size_t workspace_bytes, sh_stream_t stream)
+{
+    SH_REQUIRE(p && K > 0 && Vc > 0 && class_vertices && class_edges && feat_class, "gnn_forward_class: bad arguments");
+    const int D = p->embed_dim;
+    SH_REQUIRE(workspace_bytes >= sh_class_side_workspace_bytes(K, Vc, D), "gnn_forward_class: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tensor_path = gnn_tc_supported(D, Vc) && getenv("SCHEMANET_GNN_SIMT") == nullptr;
+    if (!tensor_path)
+        return sh_dev_gnn_forward(p, K, Vc, nullptr, class_ingredients, class_vertices, Vc, class_edges, (int64_t)Vc * Vc, Vc,
+                                  nullptr, feat_class, workspace, workspace_bytes, stream);
+    const size_t slab = align_up((size_t)K * Vc * D * sizeof(float), 256);
+    const int chunks = pool_chunks(Vc);
+    char *ws = (char *)workspace;
+    float *partial = (float *)(ws + 2 * slab);
+    char *tc_ws = ws + 2 * slab + align_up((size_t)K * chunks * D * sizeof(float), 256) + align_up((size_t)K * D * sizeof(float), 256);
+    if (gnn_class_forward_tc(p, K, Vc, class_vertices, class_edges, class_ingredients, prune_threshold, chunks, partial, tc_ws, st))
+        return 1;
+    return launch_pool_fc(p, partial, K, chunks, Vc, nullptr, feat_class, st);
 }
 
 extern "C" int sh_dev_similarity(const float *feat_instance, const float *feat_class, int B, int K, int D, int kind,

@@ -36,7 +36,8 @@ constexpr int kBBytes = G_BN * G_BK * 4;                 // 32 KB
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // hi + lo of both operands: 96 KB
 constexpr int kBarOffset = G_STAGES * kStageBytes;
 constexpr int kParamOffset = kBarOffset + 256;              // bias / gamma / beta of the fused LayerNorm epilogue
-constexpr int kSmemTotal = kParamOffset + 3 * G_BN * 4 + 1024;
+constexpr int kStageOutOffset = kParamOffset + 3 * G_BN * 4;   // per-epilogue-warp 32x33 fp32 transpose buffers
+constexpr int kSmemTotal = kStageOutOffset + 4 * 32 * 33 * 4 + 1024;
 
 enum { EPI_STORE_SPLIT = 0, EPI_LN_RELU_T_SPLIT = 1, EPI_LN_RELU_ROWS = 2 };
 
@@ -45,8 +46,11 @@ struct GemmTcArgs {
     int rows_per_graph;    // n_fixed
     int M_total;           // rows of the A operand per batch entry
     int K_total;           // reduction length upper bound
-    const int32_t *sizes;  // [G] n_g or null
-    int batched_b;         // 1: B operand indexed by the graph, 0: shared (weights)
+    const int32_t *k_sizes;   // adj GEMM: [G] active size n_g of each graph (rows and reduction range) or null
+    const int32_t *row_sizes; // epilogue: [graphs] number of real rows per graph (masks LayerNorm outputs) or null
+    int identity_tail;        // adj GEMM: rows >= n_g carry an identity diagonal (class graphs compacted to their
+                              // un-pruned vertices): such row blocks only visit their own diagonal k-blocks
+    int batched_b;            // 1: B operand indexed by the graph, 0: shared (weights)
     // epilogue
     float *out_hi, *out_lo;      // EPI_STORE_SPLIT: Y hi/lo [G, n_fixed, 256]; EPI_LN_RELU_T_SPLIT: H^T hi/lo [G, 256, ldk]
     float *out_rows;             // EPI_LN_RELU_ROWS: H [G*n_fixed, 256]
@@ -59,6 +63,37 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo)
 {
     hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
     lo = x - hi;
+}
+
+// A warp holds a 32 (rows, one per lane) x 32 (columns) fp32 chunk in registers (the TMEM layout).  Writing it row-major
+// straight from registers would issue 16-byte pieces of 32 different rows per instruction; going through a padded
+// shared-memory tile lets 8 lanes cover one 128-byte row segment, i.e. every store instruction writes 4 full lines.
+// kSplit: write hi/lo (x & 0xffffe000, x - hi) to two arrays instead of x to one.
+template <bool kSplit>
+__device__ __forceinline__ void store_chunk_rows(float *tile /* [32][33] */, const float (&v)[32], int lane, float *dst_hi,
+                                                 float *dst_lo, size_t row_stride, int rows_valid)
+{
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = v[j];
+    __syncwarp();
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;   // 4 rows per instruction, 8 lanes x float4 per row
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 4) {
+        const int r = r0 + sub;
+        if (r < rows_valid) {
+            const float *t = tile + r * 33 + c4;
+            const float4 x = make_float4(t[0], t[1], t[2], t[3]);
+            if (kSplit) {
+                float4 h, l;
+                split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+                *reinterpret_cast<float4 *>(dst_hi + (size_t)r * row_stride + c4) = h;
+                *reinterpret_cast<float4 *>(dst_lo + (size_t)r * row_stride + c4) = l;
+            } else {
+                *reinterpret_cast<float4 *>(dst_hi + (size_t)r * row_stride + c4) = x;
+            }
+        }
+    }
 }
 
 template <int EPI>
@@ -74,6 +109,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 2);
     float *s_bias = (float *)(smem + kParamOffset), *s_gamma = s_bias + G_BN, *s_beta = s_gamma + G_BN;
+    float *s_out = (float *)(smem + kStageOutOffset);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (EPI != EPI_STORE_SPLIT)
@@ -97,9 +133,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
 #define TILE_LOOP_BEGIN                                                                                   \
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {                                                 \
         const int g = t / mb_per, mb = t % mb_per;                                                        \
-        const int n_g = (a.sizes && a.G > 1) ? a.sizes[g] : a.K_total;                                    \
-        if (a.G > 1 && mb * G_BM >= n_g) continue;                                                        \
-        const int kblocks = ceil_div(a.G > 1 ? n_g : a.K_total, G_BK);
+        const int n_g = (a.k_sizes && a.G > 1) ? a.k_sizes[g] : a.K_total;                                \
+        if (a.G > 1 && !a.identity_tail && mb * G_BM >= n_g) continue;                                    \
+        /* k-blocks [0, kA) cover the active range; with identity_tail a row block that holds rows >= n_g  \
+           additionally visits the k-blocks of its own diagonal that are not in [0, kA) */                 \
+        const int kA = (a.G > 1 && a.identity_tail && mb * G_BM >= n_g) ? 0 : ceil_div(n_g, G_BK);         \
+        int k2s = 0, k2c = 0;                                                                             \
+        if (a.identity_tail && (mb + 1) * G_BM > n_g) {                                                   \
+            k2s = max(kA, mb * (G_BM / G_BK));                                                            \
+            k2c = max(0, min((mb + 1) * (G_BM / G_BK), ceil_div(a.K_total, G_BK)) - k2s);                  \
+        }                                                                                                 \
+        const int kblocks = kA + k2c;                                                                     \
+        if (kblocks == 0) continue;
 #define TILE_LOOP_END }
 
     if (warp == 0) {
@@ -107,7 +152,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             TILE_LOOP_BEGIN
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kidx = 0; kidx < kblocks; ++kidx) {
+                    const int kb = kidx < kA ? kidx : k2s + (kidx - kA);
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *s = smem + stage * kStageBytes;
                     mbar_arrive_expect_tx(&full[stage], kStageBytes);
@@ -161,29 +207,22 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
             const int m = mb * G_BM + row_in_tile;           // row inside this batch entry
             if (EPI == EPI_STORE_SPLIT) {
                 // Y[g, m, :] as hi/lo (row-major: the K-major A operand of the linear GEMM)
-                const bool valid = m < a.rows_per_graph;
-                float *oh = a.out_hi + ((size_t)g * a.rows_per_graph + m) * G_BN;
-                float *ol = a.out_lo + ((size_t)g * a.rows_per_graph + m) * G_BN;
+                // warp-level view: this warp owns rows [mb*128 + wq*32, +32) of graph g
+                const int m_warp = mb * G_BM + wq * 32;
+                const int rows_valid = min(32, a.rows_per_graph - m_warp);
+                float *oh = a.out_hi + ((size_t)g * a.rows_per_graph + m_warp) * G_BN;
+                float *ol = a.out_lo + ((size_t)g * a.rows_per_graph + m_warp) * G_BN;
 #pragma unroll 1
                 for (int c = 0; c < G_BN / 32; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-                    if (valid) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float4 h, l;
-                            split_tf32(v[4 * q + 0], h.x, l.x); split_tf32(v[4 * q + 1], h.y, l.y);
-                            split_tf32(v[4 * q + 2], h.z, l.z); split_tf32(v[4 * q + 3], h.w, l.w);
-                            *reinterpret_cast<float4 *>(oh + c * 32 + 4 * q) = h;
-                            *reinterpret_cast<float4 *>(ol + c * 32 + 4 * q) = l;
-                        }
-                    }
+                    store_chunk_rows<true>(s_out + wq * 32 * 33, v, lane, oh + c * 32, ol + c * 32, G_BN, rows_valid);
                 }
             } else {
                 // z = acc + bias; LayerNorm over the 256 columns this thread owns; ReLU   (gnn.py:31,45)
                 const int gg = m / a.rows_per_graph, i = m % a.rows_per_graph;   // flattened rows -> (graph, node)
                 const bool in_range = m < a.M_total;
-                const int n_node = (in_range && a.sizes) ? a.sizes[gg] : a.rows_per_graph;
+                const int n_node = (in_range && a.row_sizes) ? a.row_sizes[gg] : a.rows_per_graph;
                 const bool valid = in_range && i < n_node;
                 float sum = 0.0f;
 #pragma unroll 1
@@ -214,12 +253,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                         v[j] = fmaxf((z - mean) * rstd * s_gamma[n] + s_beta[n], 0.0f);
                     }
                     if (EPI == EPI_LN_RELU_ROWS) {
-                        if (valid) {
-                            float *o = a.out_rows + (size_t)m * G_BN + c * 32;
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                *reinterpret_cast<float4 *>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        }
+                        // rows of masked nodes are never read downstream (pooling stops at n_g): store all rows in range
+                        const int m_warp = mb * G_BM + wq * 32;
+                        store_chunk_rows<false>(s_out + wq * 32 * 33, v, lane, a.out_rows + (size_t)m_warp * G_BN + c * 32,
+                                                nullptr, G_BN, min(32, a.M_total - m_warp));
                     } else {
                         // H^T[gg, n, i] as hi/lo: lanes hold consecutive nodes i -> coalesced 128-byte stores; nodes
                         // beyond n_g are written as zeros (they are the zero-padded K range of the next adj GEMM)
@@ -336,6 +373,113 @@ pool_rows_kernel(const float *__restrict__ H, const float *__restrict__ vertex_w
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// class side: compaction of each class graph to its un-pruned vertices
+// ---------------------------------------------------------------------------------------------------------------
+// A vertex whose normalised weight is <= prune_node_threshold has an all-zero row and column in class_edges
+// (schema_net.py:157-166), so in ((E+E^T)/2 + I) X it only keeps its own feature.  Vertices are therefore reordered
+// "active first" (stable), the adjacency is built for the active x active corner only, and the GEMM's row blocks of
+// inactive vertices visit just their identity diagonal -- same result, a fraction of the flops and bytes.
+// One CTA per class: stable partition by prefix sums over Vc flags.
+__global__ void __launch_bounds__(1024)
+class_perm_kernel(const float *__restrict__ cv, const int64_t *__restrict__ ci, int Vc, float thr, int prune,
+                  int32_t *__restrict__ n_act, int32_t *__restrict__ old_of_new, int64_t *__restrict__ pid,
+                  float *__restrict__ pvw)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int base_act, total_act;
+    const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *cvk = cv + (size_t)k * Vc;
+    if (tid == 0) base_act = 0;
+    __syncthreads();
+    // pass 1: count active; pass 2: place.  Chunks of blockDim vertices keep the partition stable.
+    int total = 0;
+    for (int i0 = 0; i0 < Vc; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        total += (i < Vc && (!prune || cvk[i] > thr)) ? 1 : 0;
+    }
+    total = (int)warp_sum((float)total);   // counts <= 1024 per warp: exact in fp32
+    if (lane == 0) warp_tot[warp] = total;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w];
+        total_act = t;
+        n_act[k] = t;
+    }
+    __syncthreads();
+    const int nA = total_act;
+    int done_act = 0, done_in = 0;   // running offsets (uniform across the block)
+    for (int i0 = 0; i0 < Vc; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        const bool in = i < Vc;
+        const bool act = in && (!prune || cvk[i] > thr);
+        const unsigned bal = __ballot_sync(kFull, act);
+        const unsigned bal_in = __ballot_sync(kFull, in);
+        const int before = __popc(bal & ((1u << lane) - 1));
+        const int before_in = __popc(bal_in & ((1u << lane) - 1));
+        __syncthreads();
+        if (lane == 0) warp_tot[warp] = __popc(bal) | (__popc(bal_in) << 16);
+        __syncthreads();
+        int wa = 0, wi = 0, ta = 0, ti = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            const int a_ = warp_tot[w] & 0xffff, n_ = warp_tot[w] >> 16;
+            if (w < warp) { wa += a_; wi += n_; }
+            ta += a_; ti += n_;
+        }
+        if (in) {
+            const int rank_act = done_act + wa + before;
+            const int rank_inact = done_in + (wi - wa) + (before_in - before);
+            const int pos = act ? rank_act : nA + rank_inact;
+            old_of_new[(size_t)k * Vc + pos] = i;
+            pid[(size_t)k * Vc + pos] = ci[(size_t)k * Vc + i];
+            pvw[(size_t)k * Vc + pos] = cvk[i];
+        }
+        done_act += ta;
+        done_in += ti - ta;
+    }
+}
+
+// Compacted class adjacency as hi/lo.  Only the parts the GEMM reads are written: the active corner (plus its padding
+// up to the tile edges) and the 128x128 diagonal blocks of row blocks that contain inactive vertices.
+__global__ void __launch_bounds__(256)
+class_adj_prep_kernel(const float *__restrict__ ce, int Vc, int ldk, const int32_t *__restrict__ n_act,
+                      const int32_t *__restrict__ old_of_new, float *__restrict__ adj_hi, float *__restrict__ adj_lo)
+{
+    __shared__ float tile[32][33];
+    const int k = blockIdx.z;
+    const int nA = n_act[k];
+    const int pi0 = blockIdx.y * 32, pj0 = blockIdx.x * 32;
+    const int rowsA = min(Vc, (nA + G_BM - 1) / G_BM * G_BM), colsA = (nA + G_BK - 1) / G_BK * G_BK;
+    const int mb = pi0 / G_BM;
+    const bool in_a = pi0 < rowsA && pj0 < colsA;
+    const bool in_b = (mb + 1) * G_BM > nA && pj0 / G_BM == mb;
+    if (!in_a && !in_b) return;
+    const float *cek = ce + (size_t)k * Vc * Vc;
+    const int32_t *old = old_of_new + (size_t)k * Vc;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const bool any_active = pi0 < nA && pj0 < nA;
+    if (any_active) {
+        for (int r = ty; r < 32; r += 8) {      // transposed tile: ce[old[pj0 + r]][old[pi0 + tx]]
+            const int pj = pj0 + r, pi = pi0 + tx;
+            tile[r][tx] = (pj < nA && pi < nA) ? cek[(size_t)old[pj] * Vc + old[pi]] : 0.0f;
+        }
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int pi = pi0 + r, pj = pj0 + tx;
+        if (pi < Vc && pj < ldk) {
+            float v = (pi == pj) ? 1.0f : 0.0f;
+            if (pi < nA && pj < nA) v = (cek[(size_t)old[pi] * Vc + old[pj]] + tile[tx][r]) / 2.0f + v;
+            float h, l;
+            split_tf32(v, h, l);
+            const size_t o = ((size_t)k * Vc + pi) * ldk + pj;
+            adj_hi[o] = h;
+            adj_lo[o] = l;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------------
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
@@ -345,14 +489,44 @@ bool gnn_tc_supported(int D, int n_fixed)
     return D == G_BN && n_fixed >= 32 && encode_tiled_fn() != nullptr;
 }
 
+struct TcBuffers {
+    float *adj_hi, *adj_lo, *xt_hi, *xt_lo, *y_hi, *y_lo, *w_hi, *w_lo, *h_rows;
+    int32_t *n_act, *old_of_new;
+    int64_t *pid;
+    float *pvw;
+    int ldk;
+    size_t bytes;
+};
+
+static TcBuffers carve_tc(void *base, int G, int n_fixed, int D)
+{
+    TcBuffers b{};
+    b.ldk = (n_fixed + 3) / 4 * 4;
+    char *p = (char *)base;
+    size_t off = 0;
+    const size_t adj_b = al256((size_t)G * n_fixed * b.ldk * 4), xt_b = al256((size_t)G * D * b.ldk * 4);
+    const size_t y_b = al256((size_t)G * n_fixed * D * 4), w_b = al256((size_t)D * D * 4);
+    b.adj_hi = (float *)(p + off); off += adj_b;
+    b.adj_lo = (float *)(p + off); off += adj_b;
+    b.xt_hi = (float *)(p + off); off += xt_b;
+    b.xt_lo = (float *)(p + off); off += xt_b;
+    b.y_hi = (float *)(p + off); off += y_b;
+    b.y_lo = (float *)(p + off); off += y_b;
+    b.w_hi = (float *)(p + off); off += w_b;
+    b.w_lo = (float *)(p + off); off += w_b;
+    b.h_rows = (float *)(p + off); off += y_b;
+    b.n_act = (int32_t *)(p + off); off += al256((size_t)G * 4);
+    b.old_of_new = (int32_t *)(p + off); off += al256((size_t)G * n_fixed * 4);
+    b.pid = (int64_t *)(p + off); off += al256((size_t)G * n_fixed * 8);
+    b.pvw = (float *)(p + off); off += al256((size_t)G * n_fixed * 4);
+    b.bytes = off;
+    return b;
+}
+
 size_t gnn_tc_workspace_bytes(int G, int n_fixed, int D, int chunks)
 {
-    const size_t ldk = (size_t)(n_fixed + 3) / 4 * 4;
-    const size_t adj = al256((size_t)G * n_fixed * ldk * 4);
-    const size_t xt = al256((size_t)G * D * ldk * 4);
-    const size_t y = al256((size_t)G * n_fixed * D * 4);
-    const size_t w = al256((size_t)D * D * 4);
-    return 2 * adj + 2 * xt + 2 * y + 2 * w + y /* H rows */ + al256((size_t)G * chunks * D * 4) + al256((size_t)G * D * 4) + 4096;
+    (void)chunks;
+    return carve_tc(nullptr, G, n_fixed, D).bytes + 4096;
 }
 
 template <int EPI>
@@ -387,66 +561,82 @@ static int tmap3(CUtensorMap *m, const float *p, uint64_t cols, uint64_t rows, u
     return 0;
 }
 
+// All GNN layers given a prepared hi/lo adjacency in b.adj_*.  k_sizes: active size per graph for the adjacency GEMM
+// (null = n_fixed); identity_tail: see GemmTcArgs; row_sizes: real rows per graph for masking (null = all).
+static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *k_sizes, int identity_tail,
+                         const int32_t *row_sizes, const int64_t *ids, int ld_ids, const float *vertex_w, int ld_v,
+                         const TcBuffers &b, int chunks, float *partial, cudaStream_t st)
+{
+    const int D = p->embed_dim, ldk = b.ldk;
+    {
+        dim3 grid2(ceil_div(ldk, 32), D / 32, G);
+        SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(p->embedding, ids, ld_ids, row_sizes, n_fixed, ldk, D, b.xt_hi, b.xt_lo));
+        SH_CHECK_LAUNCH();
+    }
+    CUtensorMap adjm[2], xtm[2], ym[2], wm[2];
+    if (tmap3(&adjm[0], b.adj_hi, n_fixed, n_fixed, G, ldk, (uint64_t)n_fixed * ldk, G_BM)) return 1;
+    if (tmap3(&adjm[1], b.adj_lo, n_fixed, n_fixed, G, ldk, (uint64_t)n_fixed * ldk, G_BM)) return 1;
+    if (tmap3(&xtm[0], b.xt_hi, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
+    if (tmap3(&xtm[1], b.xt_lo, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
+    if (tmap3(&ym[0], b.y_hi, D, (uint64_t)G * n_fixed, 1, D, 0, G_BM)) return 1;
+    if (tmap3(&ym[1], b.y_lo, D, (uint64_t)G * n_fixed, 1, D, 0, G_BM)) return 1;
+    if (tmap3(&wm[0], b.w_hi, D, D, 1, D, 0, G_BN)) return 1;
+    if (tmap3(&wm[1], b.w_lo, D, D, 1, D, 0, G_BN)) return 1;
+
+    for (int l = 0; l < p->num_layers; ++l) {
+        const bool last = (l == p->num_layers - 1);
+        SH_LAUNCH("gnn_split_weights", st, split_kernel<<<64, 256, 0, st>>>(p->lin_w[l], (int64_t)D * D, b.w_hi, b.w_lo));
+        SH_CHECK_LAUNCH();
+        // Y = Adj X
+        GemmTcArgs a{};
+        a.G = G; a.rows_per_graph = n_fixed; a.M_total = n_fixed; a.K_total = n_fixed;
+        a.k_sizes = k_sizes; a.identity_tail = identity_tail; a.batched_b = 1;
+        a.out_hi = b.y_hi; a.out_lo = b.y_lo;
+        CUtensorMap m1[4] = {adjm[0], adjm[1], xtm[0], xtm[1]};
+        if (launch_gemm3x<EPI_STORE_SPLIT>(m1, a, "gnn_adj_gemm_tc", st)) return 1;
+        // H = relu(LN(Y W^T + b))
+        GemmTcArgs c{};
+        c.G = 1; c.rows_per_graph = n_fixed; c.M_total = G * n_fixed; c.K_total = D; c.row_sizes = row_sizes; c.batched_b = 0;
+        c.bias = p->lin_b[l]; c.gamma = p->ln_w[l]; c.beta = p->ln_b[l]; c.eps = p->ln_eps;
+        c.out_hi = b.xt_hi; c.out_lo = b.xt_lo; c.ldk = ldk; c.out_rows = b.h_rows;
+        CUtensorMap m2[4] = {ym[0], ym[1], wm[0], wm[1]};
+        if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m2, c, "gnn_linear_ln_tc", st)) return 1; }
+        else { if (launch_gemm3x<EPI_LN_RELU_T_SPLIT>(m2, c, "gnn_linear_ln_tc", st)) return 1; }
+    }
+    dim3 grid(chunks, G);
+    SH_LAUNCH("gnn_pool_rows", st, pool_rows_kernel<<<grid, 256, 0, st>>>(b.h_rows, vertex_w, ld_v, row_sizes, n_fixed, D, chunks, partial));
+    SH_CHECK_LAUNCH();
+    return 0;
+}
+
 int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *sizes, const int64_t *ids,
                    const float *vertex_w, int ld_v, const float *edges, int64_t edge_batch_stride, int edge_ld, int chunks,
                    float *partial, void *workspace, cudaStream_t st)
 {
-    const int D = p->embed_dim;
-    const int ldk = (n_fixed + 3) / 4 * 4;
-    char *ws = (char *)workspace;
-    const size_t adj_b = al256((size_t)G * n_fixed * ldk * 4), xt_b = al256((size_t)G * D * ldk * 4);
-    const size_t y_b = al256((size_t)G * n_fixed * D * 4), w_b = al256((size_t)D * D * 4);
-    float *adj_hi = (float *)ws; ws += adj_b;
-    float *adj_lo = (float *)ws; ws += adj_b;
-    float *xt_hi = (float *)ws; ws += xt_b;
-    float *xt_lo = (float *)ws; ws += xt_b;
-    float *y_hi = (float *)ws; ws += y_b;
-    float *y_lo = (float *)ws; ws += y_b;
-    float *w_hi = (float *)ws; ws += w_b;
-    float *w_lo = (float *)ws; ws += w_b;
-    float *h_rows = (float *)ws; ws += y_b;
-
-    {
-        dim3 grid(ceil_div(ldk, 32), ceil_div(n_fixed, 32), G);
-        SH_LAUNCH("gnn_adj_prep", st, adj_prep_kernel<<<grid, 256, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, ldk, adj_hi, adj_lo));
-        SH_CHECK_LAUNCH();
-        dim3 grid2(ceil_div(ldk, 32), D / 32, G);
-        SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(p->embedding, ids, ld_v, sizes, n_fixed, ldk, D, xt_hi, xt_lo));
-        SH_CHECK_LAUNCH();
-    }
-    CUtensorMap adjm[2], xtm[2], ym[2], wm[2];
-    if (tmap3(&adjm[0], adj_hi, n_fixed, n_fixed, G, ldk, (uint64_t)n_fixed * ldk, G_BM)) return 1;
-    if (tmap3(&adjm[1], adj_lo, n_fixed, n_fixed, G, ldk, (uint64_t)n_fixed * ldk, G_BM)) return 1;
-    if (tmap3(&xtm[0], xt_hi, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
-    if (tmap3(&xtm[1], xt_lo, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
-    if (tmap3(&ym[0], y_hi, D, (uint64_t)G * n_fixed, 1, D, 0, G_BM)) return 1;
-    if (tmap3(&ym[1], y_lo, D, (uint64_t)G * n_fixed, 1, D, 0, G_BM)) return 1;
-    if (tmap3(&wm[0], w_hi, D, D, 1, D, 0, G_BN)) return 1;
-    if (tmap3(&wm[1], w_lo, D, D, 1, D, 0, G_BN)) return 1;
-
-    for (int l = 0; l < p->num_layers; ++l) {
-        const bool last = (l == p->num_layers - 1);
-        SH_LAUNCH("gnn_split_weights", st, split_kernel<<<64, 256, 0, st>>>(p->lin_w[l], (int64_t)D * D, w_hi, w_lo));
-        SH_CHECK_LAUNCH();
-        // Y = Adj X
-        GemmTcArgs a{};
-        a.G = G; a.rows_per_graph = n_fixed; a.M_total = n_fixed; a.K_total = n_fixed; a.sizes = sizes; a.batched_b = 1;
-        a.out_hi = y_hi; a.out_lo = y_lo;
-        CUtensorMap m1[4] = {adjm[0], adjm[1], xtm[0], xtm[1]};
-        if (launch_gemm3x<EPI_STORE_SPLIT>(m1, a, "gnn_adj_gemm_tc", st)) return 1;
-        // H = relu(LN(Y W^T + b))
-        GemmTcArgs b{};
-        b.G = 1; b.rows_per_graph = n_fixed; b.M_total = G * n_fixed; b.K_total = D; b.sizes = sizes; b.batched_b = 0;
-        b.bias = p->lin_b[l]; b.gamma = p->ln_w[l]; b.beta = p->ln_b[l]; b.eps = p->ln_eps;
-        b.out_hi = xt_hi; b.out_lo = xt_lo; b.ldk = ldk; b.out_rows = h_rows;
-        CUtensorMap m2[4] = {ym[0], ym[1], wm[0], wm[1]};
-        if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m2, b, "gnn_linear_ln_tc", st)) return 1; }
-        else { if (launch_gemm3x<EPI_LN_RELU_T_SPLIT>(m2, b, "gnn_linear_ln_tc", st)) return 1; }
-    }
-    dim3 grid(chunks, G);
-    SH_LAUNCH("gnn_pool_rows", st, pool_rows_kernel<<<grid, 256, 0, st>>>(h_rows, vertex_w, ld_v, sizes, n_fixed, D, chunks, partial));
+    TcBuffers b = carve_tc(workspace, G, n_fixed, p->embed_dim);
+    dim3 grid(ceil_div(b.ldk, 32), ceil_div(n_fixed, 32), G);
+    SH_LAUNCH("gnn_adj_prep", st, adj_prep_kernel<<<grid, 256, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj_hi, b.adj_lo));
     SH_CHECK_LAUNCH();
-    return 0;
+    return run_layers_tc(p, G, n_fixed, sizes, 0, sizes, ids, ld_v, vertex_w, ld_v, b, chunks, partial, st);
+}
+
+// Class side with the graphs compacted to their un-pruned vertices (see class_perm_kernel).
+int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *class_vertices, const float *class_edges,
+                         const int64_t *class_ingredients, float prune_threshold, int chunks, float *partial,
+                         void *workspace, cudaStream_t st)
+{
+    TcBuffers b = carve_tc(workspace, K, Vc, p->embed_dim);
+    SH_REQUIRE(Vc <= 65535, "class side: Vc too large");
+    const int prune = prune_threshold >= 0.0f ? 1 : 0;
+    SH_LAUNCH("class_perm_kernel", st,
+              class_perm_kernel<<<K, 1024, 0, st>>>(class_vertices, class_ingredients, Vc, prune_threshold, prune, b.n_act,
+                                                    b.old_of_new, b.pid, b.pvw));
+    SH_CHECK_LAUNCH();
+    dim3 grid(ceil_div(b.ldk, 32), ceil_div(Vc, 32), K);
+    SH_LAUNCH("class_adj_prep_kernel", st,
+              class_adj_prep_kernel<<<grid, 256, 0, st>>>(class_edges, Vc, b.ldk, b.n_act, b.old_of_new, b.adj_hi, b.adj_lo));
+    SH_CHECK_LAUNCH();
+    return run_layers_tc(p, K, Vc, b.n_act, 1, nullptr, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st);
 }
 
 }  // namespace sh

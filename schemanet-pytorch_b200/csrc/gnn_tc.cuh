@@ -11,4 +11,9 @@ int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *si
                    const float *vertex_w, int ld_v, const float *edges, int64_t edge_batch_stride, int edge_ld, int chunks,
                    float *partial, void *workspace, cudaStream_t st);
 
+// Class-side variant: graphs are compacted to their un-pruned vertices first (exact, see gnn_tc.cu).
+int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *class_vertices, const float *class_edges,
+                         const int64_t *class_ingredients, float prune_threshold, int chunks, float *partial,
+                         void *workspace, cudaStream_t st);
+
 }  // namespace sh

@@ -26,7 +26,7 @@ namespace sh {
 constexpr int kMaxL = 256;           // tokens per image supported by the shared-memory layout (reference: 196)
 constexpr int kGraphThreads = 256;   // 8 warps
 constexpr int kGraphWarps = kGraphThreads / kWarp;
-constexpr int kLaneCols = kMaxL / kWarp;   // columns / output codes owned by one lane
+constexpr int kMaxLaneCols = kMaxL / kWarp;   // columns / output codes owned by one lane (template LC <= this)
 
 struct GraphArgs {
     const int64_t *ingredients;   // [B, L]
@@ -104,15 +104,15 @@ __device__ __forceinline__ void rank_codes(GraphSmem &s, const int64_t *codes, i
 }
 
 // One row of (optionally head-averaged) attention logits: lane holds columns q = lane + 32 t.
-template <bool kFromHeads>
-__device__ __forceinline__ void load_row(const GraphArgs &a, int b, int p, int lane, float (&x)[kLaneCols])
+template <bool kFromHeads, int LC>
+__device__ __forceinline__ void load_row(const GraphArgs &a, int b, int p, int lane, float (&x)[LC])
 {
     const int L = a.L;
     if (kFromHeads) {
         const int T = L + 1;
         const float *base = a.attn + ((size_t)b * a.H * T + (size_t)(p + 1)) * T + 1;
 #pragma unroll
-        for (int t = 0; t < kLaneCols; ++t) {
+        for (int t = 0; t < LC; ++t) {
             const int q = lane + kWarp * t;
             float acc = 0.0f;
             if (q < L) {
@@ -124,7 +124,7 @@ __device__ __forceinline__ void load_row(const GraphArgs &a, int b, int p, int l
     } else {
         const float *base = a.attn + ((size_t)b * L + p) * L;
 #pragma unroll
-        for (int t = 0; t < kLaneCols; ++t) {
+        for (int t = 0; t < LC; ++t) {
             const int q = lane + kWarp * t;
             x[t] = (q < L) ? __ldg(base + q) : 0.0f;
         }
@@ -132,11 +132,12 @@ __device__ __forceinline__ void load_row(const GraphArgs &a, int b, int p, int l
 }
 
 // masked_fill(x < clamp, -inf) + softmax over the L valid columns held by the warp (schema_net.py:334-336).
-__device__ __forceinline__ void warp_softmax(float (&x)[kLaneCols], int L, int lane, float clamp, bool use_clamp)
+template <int LC>
+__device__ __forceinline__ void warp_softmax(float (&x)[LC], int L, int lane, float clamp, bool use_clamp)
 {
     float m = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < kLaneCols; ++t) {
+    for (int t = 0; t < LC; ++t) {
         const int q = lane + kWarp * t;
         if (q < L) {
             if (use_clamp && x[t] < clamp) x[t] = -INFINITY;
@@ -146,10 +147,10 @@ __device__ __forceinline__ void warp_softmax(float (&x)[kLaneCols], int L, int l
     m = warp_max(m);
     float sum = 0.0f;
 #pragma unroll
-    for (int t = 0; t < kLaneCols; ++t) {
+    for (int t = 0; t < LC; ++t) {
         const int q = lane + kWarp * t;
         // all-masked row: x - m = (-inf) - (-inf) = NaN, exactly like torch.softmax
-        x[t] = (q < L) ? expf(x[t] - m) : 0.0f;
+        x[t] = (q < L) ? __expf(x[t] - m) : 0.0f;   // ex2.approx path: ~2 ulp, NaN/-inf semantics as expf
         sum += x[t];
     }
     sum = warp_sum(sum);
@@ -158,13 +159,13 @@ __device__ __forceinline__ void warp_softmax(float (&x)[kLaneCols], int L, int l
     // most 1 ulp, far inside the 1e-5 tolerance, and 0 * (1/0) = NaN keeps the all-masked-row semantics
     const float inv = 1.0f / sum;
 #pragma unroll
-    for (int t = 0; t < kLaneCols; ++t) x[t] = x[t] * inv;
+    for (int t = 0; t < LC; ++t) x[t] = x[t] * inv;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // vertices of one image (large_scale_feat_to_v.cpp:78-125)
 // ---------------------------------------------------------------------------------------------------------------
-template <bool kFromHeads>
+template <bool kFromHeads, int LC>
 __device__ __forceinline__ void build_vertices(const GraphArgs &a, GraphSmem &s, int b)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -172,13 +173,13 @@ __device__ __forceinline__ void build_vertices(const GraphArgs &a, GraphSmem &s,
     const bool raw = (a.flags & SH_G_RAW_LOGITS) != 0;
     const bool use_clamp = raw && a.clamp_v != SH_NO_CLAMP;
     if (warp == 0) {
-        float x[kLaneCols];
+        float x[LC];
         if (kFromHeads) {
             GraphArgs a2 = a;   // row "-1" of the sliced map == the cls row (token 0) of the full map
-            load_row<true>(a2, b, -1, lane, x);
+            load_row<true, LC>(a2, b, -1, lane, x);
         } else {
 #pragma unroll
-            for (int t = 0; t < kLaneCols; ++t) {
+            for (int t = 0; t < LC; ++t) {
                 const int q = lane + kWarp * t;
                 x[t] = (q < L) ? a.attn_cls[(size_t)b * L + q] : 0.0f;
             }
@@ -186,17 +187,17 @@ __device__ __forceinline__ void build_vertices(const GraphArgs &a, GraphSmem &s,
         if (raw) {
             if (!kFromHeads && use_clamp && (a.flags & SH_G_WRITE_BACK_CLAMP)) {
 #pragma unroll
-                for (int t = 0; t < kLaneCols; ++t) {
+                for (int t = 0; t < LC; ++t) {
                     const int q = lane + kWarp * t;
                     if (q < L && x[t] < a.clamp_v) a.attn_cls[(size_t)b * L + q] = -INFINITY;   // schema_net.py:296
                 }
             }
             warp_softmax(x, L, lane, a.clamp_v, use_clamp);
 #pragma unroll
-            for (int t = 0; t < kLaneCols; ++t) x[t] = nan_to_num0(x[t]);                        // :297
+            for (int t = 0; t < LC; ++t) x[t] = nan_to_num0(x[t]);                        // :297
         }
 #pragma unroll
-        for (int t = 0; t < kLaneCols; ++t) {
+        for (int t = 0; t < LC; ++t) {
             const int q = lane + kWarp * t;
             if (q < L) s.acls[q] = x[t];
         }
@@ -235,7 +236,7 @@ __device__ __forceinline__ void build_vertices(const GraphArgs &a, GraphSmem &s,
 // ---------------------------------------------------------------------------------------------------------------
 // edges of one image (large_scale_feat_to_e.cpp:99-140); kDense selects the feat_to_e.cpp output convention
 // ---------------------------------------------------------------------------------------------------------------
-template <bool kFromHeads, bool kDense>
+template <bool kFromHeads, bool kDense, int LC>
 __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, int b)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -249,6 +250,20 @@ __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, in
     float w0 = 0.f, w1 = 0.f;
     if (!kDense) { w0 = __ldg(a.w_e); w1 = __ldg(a.w_e + 1); }
 
+    // The output codes r2 = lane + 32 t a lane owns are the same for every row of the image: keep each code's first
+    // position, its position count and its CSR offset in registers (most codes occur once -> one shared-memory read
+    // per (row, code) pair and no loop).
+    int q0[LC], qn[LC], qs[LC];
+#pragma unroll
+    for (int t = 0; t < LC; ++t) {
+        const int r2 = lane + kWarp * t;
+        const bool live = r2 < n && (!kDense || s.loc[r2] >= 0);
+        qs[t] = live ? s.start[r2] : 0;
+        qn[t] = live ? s.cnt[r2] : 0;
+        q0[t] = live ? s.pos[qs[t]] : 0;
+    }
+    const int nt = (n + kWarp - 1) / kWarp;   // lane slots in use (warp-uniform)
+
     for (;;) {
         int r1 = 0;
         if (lane == 0) r1 = atomicAdd(&s.next_row, 1);
@@ -256,48 +271,49 @@ __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, in
         if (r1 >= n) break;
         if (kDense && s.loc[r1] < 0) continue;   // code not in the label's class (feat_to_e.cpp:62-77)
 
-        float acc_a[kLaneCols], acc_g[kLaneCols];
+        float acc_a[LC], acc_g[LC];
 #pragma unroll
-        for (int t = 0; t < kLaneCols; ++t) { acc_a[t] = 0.0f; acc_g[t] = 0.0f; }
+        for (int t = 0; t < LC; ++t) { acc_a[t] = 0.0f; acc_g[t] = 0.0f; }
 
         const int k_begin = s.start[r1], k_end = s.start[r1 + 1];
-        float x[kLaneCols], xn[kLaneCols];
-        load_row<kFromHeads>(a, b, s.pos[k_begin], lane, xn);
+        float x[LC], xn[LC];
+        load_row<kFromHeads, LC>(a, b, s.pos[k_begin], lane, xn);
         for (int k = k_begin; k < k_end; ++k) {
             const int p = s.pos[k];
 #pragma unroll
-            for (int t = 0; t < kLaneCols; ++t) x[t] = xn[t];
-            if (k + 1 < k_end) load_row<kFromHeads>(a, b, s.pos[k + 1], lane, xn);   // prefetch the next row
-            float g[kLaneCols];
+            for (int t = 0; t < LC; ++t) x[t] = xn[t];
+            if (k + 1 < k_end) load_row<kFromHeads, LC>(a, b, s.pos[k + 1], lane, xn);   // prefetch the next row
+            float g[LC];
 #pragma unroll
-            for (int t = 0; t < kLaneCols; ++t) {
+            for (int t = 0; t < LC; ++t) {
                 const int q = lane + kWarp * t;
                 g[t] = (q < L) ? __ldg(a.geo + (size_t)p * L + q) : 0.0f;
             }
             if (raw) {
                 if (write_back) {
 #pragma unroll
-                    for (int t = 0; t < kLaneCols; ++t) {
+                    for (int t = 0; t < LC; ++t) {
                         const int q = lane + kWarp * t;
                         if (q < L && x[t] < a.clamp_e) a.attn[((size_t)b * L + p) * L + q] = -INFINITY;  // :335
                     }
                 }
-                warp_softmax(x, L, lane, a.clamp_e, use_clamp);
+                warp_softmax<LC>(x, L, lane, a.clamp_e, use_clamp);
             }
             __syncwarp();
 #pragma unroll
-            for (int t = 0; t < kLaneCols; ++t) {
+            for (int t = 0; t < LC; ++t) {
                 const int q = lane + kWarp * t;
                 if (q < L) { rowA[q] = x[t]; rowG[q] = g[t]; }
             }
             __syncwarp();
+            // same fp32 order as the reference: positions ascending, one scalar accumulator per (r1, r2)
 #pragma unroll
-            for (int t = 0; t < kLaneCols; ++t) {
-                const int r2 = lane + kWarp * t;
-                if (r2 < n) {
-                    const int e = s.start[r2 + 1];
-                    for (int kk = s.start[r2]; kk < e; ++kk) {
-                        const int q = s.pos[kk];
+            for (int t = 0; t < LC; ++t) {
+                if (t < nt && qn[t] > 0) {
+                    acc_a[t] = acc_a[t] + rowA[q0[t]];
+                    acc_g[t] = acc_g[t] + rowG[q0[t]];
+                    for (int kk = 1; kk < qn[t]; ++kk) {
+                        const int q = s.pos[qs[t] + kk];
                         acc_a[t] = acc_a[t] + rowA[q];
                         acc_g[t] = acc_g[t] + rowG[q];
                     }
@@ -306,42 +322,43 @@ __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, in
         }
 
         // epilogue: block mean, row normalisation, nan_to_num, 2->1 mix
-        const float c1 = (float)s.cnt[r1];
+        const float c1 = (float)(k_end - k_begin);
         float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-        for (int t = 0; t < kLaneCols; ++t) {
-            const int r2 = lane + kWarp * t;
-            if (r2 < n) {
-                if (mean) {
-                    const float denom = c1 * (float)s.cnt[r2];   // container.size() (utils.cpp:12)
+        for (int t = 0; t < LC; ++t) {
+            if (t < nt && qn[t] > 0) {
+                const float denom = c1 * (float)qn[t];          // container.size() (utils.cpp:12)
+                if (mean && denom != 1.0f) {                     // x / 1 == x: skip the IEEE division for single pairs
                     acc_g[t] = acc_g[t] / denom;
                     acc_a[t] = acc_a[t] / denom;
                 }
-                if (!kDense || s.loc[r2] >= 0) { s0 += acc_g[t]; s1 += acc_a[t]; }
+                s0 += acc_g[t];
+                s1 += acc_a[t];
             }
         }
         if (kDense) {
             const int l1 = s.loc[r1];
             float *o = a.dense_out + (size_t)b * a.n_max * a.n_max * 2;
 #pragma unroll
-            for (int t = 0; t < kLaneCols; ++t) {
+            for (int t = 0; t < LC; ++t) {
                 const int r2 = lane + kWarp * t;
-                if (r2 < n && s.loc[r2] >= 0) {
-                    float2 v = make_float2(acc_g[t], acc_a[t]);
-                    *reinterpret_cast<float2 *>(o + ((size_t)l1 * a.n_max + s.loc[r2]) * 2) = v;
-                }
+                if (t < nt && qn[t] > 0)
+                    *reinterpret_cast<float2 *>(o + ((size_t)l1 * a.n_max + s.loc[r2]) * 2) = make_float2(acc_g[t], acc_a[t]);
             }
         } else {
             s0 = warp_sum(s0);
             s1 = warp_sum(s1);
+            // one reciprocal per row and channel (<= 1 ulp from x / s); a row whose sums are finite and non-zero has
+            // only finite entries, so nan_to_num (large_scale_feat_to_e.cpp:135) is only applied to the other rows
             const float inv0 = 1.0f / s0, inv1 = 1.0f / s1;
+            const bool clean = isfinite(inv0) && isfinite(inv1) && isfinite(s0) && isfinite(s1);
             float *o = a.edges + (size_t)b * L * L + (size_t)r1 * L;
 #pragma unroll
-            for (int t = 0; t < kLaneCols; ++t) {
+            for (int t = 0; t < LC; ++t) {
                 const int r2 = lane + kWarp * t;
                 if (r2 < n) {
-                    const float v0 = nan_to_num0(acc_g[t] * inv0);   // large_scale_feat_to_e.cpp:135
-                    const float v1 = nan_to_num0(acc_a[t] * inv1);
+                    float v0 = acc_g[t] * inv0, v1 = acc_a[t] * inv1;
+                    if (!clean) { v0 = nan_to_num0(v0); v1 = nan_to_num0(v1); }
                     o[r2] = v0 * w0 + v1 * w1;                     // :140
                 } else if (r2 < L && (a.flags & SH_G_ZERO_PAD)) {
                     o[r2] = 0.0f;                                  // match.py:54 padding, produced in place
@@ -351,7 +368,7 @@ __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, in
     }
 }
 
-template <bool kFromHeads>
+template <bool kFromHeads, int LC>
 __global__ void __launch_bounds__(kGraphThreads) instance_graph_kernel(GraphArgs a)
 {
     __shared__ GraphSmem s;
@@ -361,9 +378,9 @@ __global__ void __launch_bounds__(kGraphThreads) instance_graph_kernel(GraphArgs
             if (a.num_vertices) a.num_vertices[b] = s.n;
             if (a.max_vertices) atomicMax(a.max_vertices, s.n);
         }
-        if (a.vertex_w) build_vertices<kFromHeads>(a, s, b);
+        if (a.vertex_w) build_vertices<kFromHeads, LC>(a, s, b);
         if (a.edges) {
-            build_edges<kFromHeads, false>(a, s, b);
+            build_edges<kFromHeads, false, LC>(a, s, b);
             if (a.flags & SH_G_ZERO_PAD) {   // rows n..L-1 of the [L, L] slot
                 float *o = a.edges + (size_t)b * a.L * a.L;
                 for (int i = s.n * a.L + threadIdx.x; i < a.L * a.L; i += blockDim.x) o[i] = 0.0f;
@@ -374,6 +391,7 @@ __global__ void __launch_bounds__(kGraphThreads) instance_graph_kernel(GraphArgs
 }
 
 // feat_to_e.cpp:31-127 -- only codes of the label's class, written at class-local indices, no normalisation.
+template <int LC>
 __global__ void __launch_bounds__(kGraphThreads) dense_edges_kernel(GraphArgs a)
 {
     __shared__ GraphSmem s;
@@ -389,7 +407,7 @@ __global__ void __launch_bounds__(kGraphThreads) dense_edges_kernel(GraphArgs a)
             s.loc[threadIdx.x] = found;
         }
         __syncthreads();
-        build_edges<false, true>(a, s, b);
+        build_edges<false, true, LC>(a, s, b);
         __syncthreads();
     }
 }
@@ -476,8 +494,12 @@ extern "C" int sh_dev_instance_graphs(const int64_t *ingredients, float *attn, f
     a.w_v = w_vertex; a.w_e = w_edge; a.flags = flags;
     a.ids = ids; a.vertex_w = vertex_w; a.edges = edges; a.num_vertices = num_vertices; a.max_vertices = max_vertices;
     const int grid = B;
-    if (heads) SH_LAUNCH("instance_graph_kernel", (cudaStream_t)stream, instance_graph_kernel<true><<<grid, kGraphThreads, 0, (cudaStream_t)stream>>>(a));
-    else SH_LAUNCH("instance_graph_kernel", (cudaStream_t)stream, instance_graph_kernel<false><<<grid, kGraphThreads, 0, (cudaStream_t)stream>>>(a));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool narrow = L <= 7 * kWarp;   // 196 tokens: 7 columns per lane instead of 8
+    if (heads && narrow) SH_LAUNCH("instance_graph_kernel", st, instance_graph_kernel<true, 7><<<grid, kGraphThreads, 0, st>>>(a));
+    else if (heads) SH_LAUNCH("instance_graph_kernel", st, instance_graph_kernel<true, 8><<<grid, kGraphThreads, 0, st>>>(a));
+    else if (narrow) SH_LAUNCH("instance_graph_kernel", st, instance_graph_kernel<false, 7><<<grid, kGraphThreads, 0, st>>>(a));
+    else SH_LAUNCH("instance_graph_kernel", st, instance_graph_kernel<false, 8><<<grid, kGraphThreads, 0, st>>>(a));
     SH_CHECK_LAUNCH();
     return 0;
 }
@@ -503,7 +525,8 @@ extern "C" int sh_dev_feat_to_e(const int64_t *ingredients, const float *attn, c
     a.ingredients = ingredients; a.attn = const_cast<float *>(attn); a.geo = geo_sim;
     a.B = B; a.L = L; a.flags = mean ? 0 : SH_G_SUM; a.clamp_v = a.clamp_e = SH_NO_CLAMP;
     a.class_ingredients = class_ingredients; a.label = label; a.n_max = n_max; a.dense_out = out;
-    SH_LAUNCH("dense_edges_kernel", (cudaStream_t)stream, dense_edges_kernel<<<B, kGraphThreads, 0, (cudaStream_t)stream>>>(a));
+    if (L <= 7 * kWarp) SH_LAUNCH("dense_edges_kernel", (cudaStream_t)stream, dense_edges_kernel<7><<<B, kGraphThreads, 0, (cudaStream_t)stream>>>(a));
+    else SH_LAUNCH("dense_edges_kernel", (cudaStream_t)stream, dense_edges_kernel<8><<<B, kGraphThreads, 0, (cudaStream_t)stream>>>(a));
     SH_CHECK_LAUNCH();
     return 0;
 }

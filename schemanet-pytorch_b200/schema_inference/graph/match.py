@@ -58,6 +58,12 @@ class Matcher(nn.Module):
             if self.mutate_inputs:
                 for i in range(len(ids)):
                     ids[i], vw[i], ed[i] = pid[i], pw[i], pe[i]
-        feat_kg = self.gnn(nodes=class_dict["class_vertices"], edges=class_dict["class_edges"],
-                           ingredients=class_dict["class_ingredients"])
+        if hasattr(class_dict, "prune_node_threshold") and class_dict["class_edges"].is_contiguous():
+            # the atlas came from SchemaNet.get_atlas(): pruned vertices are known to be isolated
+            self.gnn._check_inference()
+            feat_kg = native.gnn_forward_class(self.gnn.param_pack(), class_dict["class_vertices"], class_dict["class_edges"],
+                                               class_dict["class_ingredients"], class_dict.prune_node_threshold)
+        else:
+            feat_kg = self.gnn(nodes=class_dict["class_vertices"], edges=class_dict["class_edges"],
+                               ingredients=class_dict["class_ingredients"])
         return self.similarity(feat_instance, feat_kg)

@@ -25,6 +25,12 @@ class InstanceGraphs(dict):
     sizes: List[int] = None
 
 
+class Atlas(dict):
+    """The dict `SchemaNet.get_atlas` returns, plus the prune threshold the class graphs were built with: vertices at
+    or below it have all-zero edge rows/columns, which lets `Matcher` skip them (same result, fewer flops)."""
+    prune_node_threshold: float = None
+
+
 class SchemaNet(nn.Module):
     """IR-Atlas (class graphs) and instance IR-Graph generation.
 
@@ -134,11 +140,10 @@ class SchemaNet(nn.Module):
             raise NotImplementedError("schemanet_b200: the atlas backward pass is not built yet (SURVEY.md section 8 f3); "
                                       "call under torch.no_grad() or with detach=True")
         class_vertices, class_edges = self._atlas(True)
-        return {
-            "class_vertices": class_vertices,
-            "class_edges": class_edges,
-            "class_ingredients": self.class_ingredients.tensor
-        }
+        atlas = Atlas(class_vertices=class_vertices, class_edges=class_edges,
+                      class_ingredients=self.class_ingredients.tensor)
+        atlas.prune_node_threshold = self.prune_node_threshold
+        return atlas
 
     def _geo(self, device) -> torch.Tensor:
         return graph_utils.pair_wise_point_sim(self.feat_h, self.feat_w, self.dist_alpha, self.dist_pow, device)

@@ -62,8 +62,10 @@ class SchemaHead:
         vw, ew, ci = sn.vertex_weights.tensor, sn.edge_weights.tensor, sn.class_ingredients.tensor
         K = vw.shape[0]
         if self.class_shard is None:
-            cv, ce = native.class_atlas(vw, ew, sn.prune_node_threshold, True, sn.remove_self_loop)
-            return gnn(nodes=cv, edges=ce, ingredients=ci)
+            gnn._check_inference()
+            cv, ce, f_kg = native.class_side(gnn.param_pack(), vw, ew, ci, sn.prune_node_threshold, True, sn.remove_self_loop)
+            self.atlas = {"class_vertices": cv, "class_edges": ce, "class_ingredients": ci}
+            return f_kg
         import torch.distributed as dist
         rank, world = self.class_shard
         per = (K + world - 1) // world
@@ -71,8 +73,10 @@ class SchemaHead:
         D = gnn.embed_dim
         local = torch.zeros(per, D, dtype=torch.float32, device=vw.device)
         if k1 > k0:
-            cv, ce = native.class_atlas(vw[k0:k1], ew[k0:k1], sn.prune_node_threshold, True, sn.remove_self_loop)
-            local[:k1 - k0] = gnn(nodes=cv, edges=ce, ingredients=ci[k0:k1])
+            gnn._check_inference()
+            _, _, f = native.class_side(gnn.param_pack(), vw[k0:k1], ew[k0:k1], ci[k0:k1].contiguous(),
+                                        sn.prune_node_threshold, True, sn.remove_self_loop)
+            local[:k1 - k0] = f
         full = torch.empty(world * per, D, dtype=torch.float32, device=vw.device)
         dist.all_gather_into_tensor(full, local)              # the path's only collective: K*D*4 bytes over NVLink
         return full[:K]
@@ -106,3 +110,47 @@ class SchemaHead:
         return {"pred": pred, "ingredients": ingredients, "graphs": graphs, "feat_instance": f_inst, "feat_class": f_kg}
 
     __call__ = forward
+
+
+class HostPipeline:
+    """Host-buffer front end of `SchemaHead`: the call a serving loop makes when the backbone taps arrive in (pinned)
+    host memory.  `submit()` enqueues, for one batch, the H2D copies on a copy stream, the whole head on the compute
+    stream and the D2H copy of the logits into a pinned buffer; two staging slots let the copies of batch i+1 overlap
+    the kernels of batch i.  `result(ticket)` waits for that batch only.  Every batch's inputs cross PCIe exactly once.
+    """
+
+    def __init__(self, head: SchemaHead, device, slots: int = 2):
+        self.head, self.device, self.slots = head, device, slots
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.staging = [None] * slots
+        self.h2d_done = [torch.cuda.Event() for _ in range(slots)]
+        self.compute_done = [torch.cuda.Event() for _ in range(slots)]
+        self.d2h_done = [torch.cuda.Event() for _ in range(slots)]
+        self.out_host = [None] * slots
+        self.ticket = 0
+
+    def submit(self, mid_feat: torch.Tensor, attn: torch.Tensor, attn_cls: torch.Tensor) -> int:
+        s = self.ticket % self.slots
+        if self.staging[s] is None:
+            self.staging[s] = tuple(torch.empty_like(t, device=self.device) for t in (mid_feat, attn, attn_cls))
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.compute_done[s])          # slot is free once its last consumer finished
+            for dst, src in zip(self.staging[s], (mid_feat, attn, attn_cls)):
+                dst.copy_(src, non_blocking=True)
+            self.h2d_done[s].record(self.copy_stream)
+        main.wait_event(self.h2d_done[s])
+        out = self.head(*self.staging[s])
+        self.compute_done[s].record(main)
+        pred = out["pred"]
+        if self.out_host[s] is None:
+            self.out_host[s] = torch.empty(pred.shape, dtype=pred.dtype).pin_memory()
+        self.out_host[s].copy_(pred, non_blocking=True)
+        self.d2h_done[s].record(main)
+        self.ticket += 1
+        return self.ticket - 1
+
+    def result(self, ticket: int) -> torch.Tensor:
+        s = ticket % self.slots
+        self.d2h_done[s].synchronize()
+        return self.out_host[s]

@@ -25,7 +25,8 @@ SYMBOLS = [
     "sh_discretize_workspace_bytes", "sh_dev_discretize", "sh_discretize_stats",
     "sh_dev_instance_graphs", "sh_dev_feat_to_v_attr", "sh_dev_feat_to_e",
     "sh_dev_class_atlas",
-    "sh_gnn_workspace_bytes", "sh_dev_gnn_forward", "sh_dev_similarity",
+    "sh_gnn_workspace_bytes", "sh_dev_gnn_forward", "sh_dev_similarity", "sh_class_side_workspace_bytes",
+    "sh_dev_class_side", "sh_dev_gnn_forward_class",
     "sh_host_feat_to_instance_v", "sh_host_feat_to_instance_e", "sh_host_feat_to_v_attr", "sh_host_feat_to_e",
 ]
 
@@ -70,6 +71,11 @@ def lib():
         L.sh_dev_gnn_forward.argtypes = [ctypes.POINTER(GnnParams), i32, i32, vp, vp, vp, i32, vp, i64, i32, vp, vp, vp,
                                          ctypes.c_size_t, vp]
         L.sh_dev_similarity.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+        L.sh_class_side_workspace_bytes.restype = ctypes.c_size_t
+        L.sh_class_side_workspace_bytes.argtypes = [i32, i32, i32]
+        L.sh_dev_gnn_forward_class.argtypes = [ctypes.POINTER(GnnParams), i32, i32, vp, vp, vp, f32, vp, vp, ctypes.c_size_t, vp]
+        L.sh_dev_class_side.argtypes = [ctypes.POINTER(GnnParams), vp, vp, vp, i32, i32, f32, i32, i32, vp, vp, vp, vp,
+                                        ctypes.c_size_t, vp]
         L.sh_host_feat_to_instance_v.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp, vp]
         L.sh_host_feat_to_instance_e.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, vp]
         L.sh_host_feat_to_v_attr.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
@@ -309,6 +315,41 @@ def gnn_forward(params, G, n_fixed, sizes, ids, vertex_w, ld_v, edges, edge_batc
     check(lib().sh_dev_gnn_forward(ctypes.byref(params.struct), G, n_fixed, ptr(sizes), ptr(ids), ptr(vertex_w), ld_v,
                                    ptr(edges), edge_batch_stride, edge_ld, ptr(mean_div), ptr(out), ptr(ws), ws.numel(),
                                    stream()))
+    return out
+
+
+def class_side(params, vertex_weights, edge_weights, class_ingredients, prune_threshold=None, prune_in_place=True,
+               remove_self_loop=False):
+    """get_atlas() + GNN(class graphs) in one call -> (class_vertices, class_edges, feat_class [K, D])."""
+    require_cuda(vertex_weights, edge_weights, class_ingredients)
+    K, Vc = vertex_weights.shape
+    vw = _f32c(vertex_weights.detach())
+    ew = edge_weights.detach()
+    if ew.dtype != torch.float32 or not ew.is_contiguous():
+        raise RuntimeError("edge_weights must be a contiguous float32 CUDA tensor")
+    ci = _i64c(class_ingredients)
+    D = params.embed_dim
+    cv = torch.empty(K, Vc, dtype=torch.float32, device=vw.device)
+    ce = torch.empty(K, Vc, Vc, dtype=torch.float32, device=vw.device)
+    out = torch.empty(K, D, dtype=torch.float32, device=vw.device)
+    ws = _workspace("class", lib().sh_class_side_workspace_bytes(K, Vc, D), vw.device)
+    thr = -1.0 if prune_threshold is None else float(prune_threshold)
+    check(lib().sh_dev_class_side(ctypes.byref(params.struct), ptr(vw), ptr(ew), ptr(ci), K, Vc, thr, int(prune_in_place),
+                                  int(remove_self_loop), ptr(cv), ptr(ce), ptr(out), ptr(ws), ws.numel(), stream()))
+    return cv, ce, out
+
+
+def gnn_forward_class(params, class_vertices, class_edges, class_ingredients, prune_threshold=None):
+    """GNN.forward on get_atlas()'s class graphs -> [K, D]; pruned vertices (all-zero edge rows/columns) are skipped."""
+    require_cuda(class_vertices, class_edges, class_ingredients)
+    K, Vc = class_vertices.shape
+    D = params.embed_dim
+    out = torch.empty(K, D, dtype=torch.float32, device=class_vertices.device)
+    ws = _workspace("class", lib().sh_class_side_workspace_bytes(K, Vc, D), class_vertices.device)
+    thr = -1.0 if prune_threshold is None else float(prune_threshold)
+    check(lib().sh_dev_gnn_forward_class(ctypes.byref(params.struct), K, Vc, ptr(_f32c(class_vertices.detach())),
+                                         ptr(_f32c(class_edges.detach())), ptr(_i64c(class_ingredients)), thr, ptr(out), ptr(ws),
+                                         ws.numel(), stream()))
     return out
 
 

@@ -349,6 +349,73 @@ def test_gnn_tensor_core_path_vs_oracle(K, Vc, masked):
     rel_close(got, want, what="gnn tensor-core path")
 
 
+class _FakeBackbone(torch.nn.Module):
+    """Stands in for the reference's JIT backbone: returns fixed `mid_feat` / `extracted` taps."""
+
+    def __init__(self, mid, extracted):
+        super().__init__()
+        self.mid, self.extracted = mid, extracted
+
+    def forward(self, x):
+        return {"mid_feat": self.mid, "extracted": self.extracted}
+
+
+def test_predictor_with_ingredient_wrapper_vs_oracle():
+    """SchemaNetPredictor end to end (graph/__init__.py:37-57) on top of IngredientModelWrapper
+    (ingredient_model_wrapper.py:43-69): every key of the wrapper's dict and the predictor's dict, requires_graph too."""
+    from discretization import Discretization, DiscretizationJitWrapper
+    from schema_inference.graph import SchemaNetPredictor
+    from schema_inference.utils import IngredientModelWrapper
+    B, d, M, K, Vc, D, H = 6, 64, 96, 5, 96, 256, 3
+    vocab, mid, _, _ = ho.synth_inputs(B, d, M, seed=501)
+    gen = torch.Generator().manual_seed(502)
+    extracted = 0.5 * torch.randn(B * H, 197, 197, generator=gen)
+    schema = ho.synth_schema(M, K, Vc, seed=503)
+    gnn = ho.synth_gnn(M, D, seed=504)
+    attn, attn_cls = ho.attention_prologue(extracted, B)
+    ref = ho.head_forward(mid, attn, attn_cls, vocab, schema, gnn, ho.HEAD_CFG)
+    seq_ref, _ = ho.discretize_with_cls(mid, vocab)
+
+    disc = Discretization(M, d, uniform_range=[0, 1])
+    with torch.no_grad():
+        disc.vocabulary.weight.copy_(vocab)
+    sn, m = build_modules(schema=schema, gnn=gnn, M=M, K=K, Vc=Vc, D=D)
+    wrapper = IngredientModelWrapper(_FakeBackbone(mid.cuda(), extracted.cuda()), DiscretizationJitWrapper(disc)).cuda()
+    pred = SchemaNetPredictor(wrapper, sn, m).cuda().eval()
+    with torch.no_grad():
+        w = wrapper(torch.zeros(B, 3, 224, 224, device="cuda"))
+        out = pred(torch.zeros(B, 3, 224, 224, device="cuda"), requires_graph=True)
+    assert list(w.keys()) == ["cls_token", "feat", "feat_origin", "ingredients", "attn", "attn_cls"]
+    assert torch.equal(w["ingredients"].cpu(), ref["ingredients"])
+    assert torch.equal(w["cls_token"].cpu(), mid[:1].transpose(0, 1)) and torch.equal(w["feat_origin"].cpu(), mid[1:].transpose(0, 1))
+    assert torch.equal(w["feat"].cpu(), seq_ref[1:].transpose(0, 1))
+    rel_close(w["attn"], attn, 1e-6, "attn")
+    rel_close(w["attn_cls"], attn_cls, 1e-6, "attn_cls")
+    assert list(out.keys())[:4] == ["pred", "class_vertices", "class_edges", "class_ingredients"]
+    rel_close(out["pred"], ref["pred"], what="predictor logits")
+    rel_close(out["class_edges"], ref["class_edges"], 2e-6, "class_edges")
+    for k in ("instance_ingredients", "instance_vertices", "instance_edges", "ingredients", "attn_cls"):
+        assert k in out
+
+
+@pytest.mark.parametrize("name,B,K", [("cfg3", 6, 4), ("cfg4", 3, 5)])
+def test_large_config_slices_vs_oracle(name, B, K):
+    """BASELINE configs[2] / configs[3] shapes (DeiT-Base d=768; ImageNet M=8000, Vc=500, D=1024) on a slice of the
+    batch and of the class set that the CPU oracle finishes in seconds."""
+    from schemanet_b200.head import SchemaHead
+    c = dict(ho.CONFIGS[name], B=B, K=K)
+    vocab, mid, attn, attn_cls = ho.synth_inputs(c["B"], c["d"], c["M"], seed=700 + K)
+    schema = ho.synth_schema(c["M"], c["K"], c["Vc"], seed=701)
+    gnn = ho.synth_gnn(c["M"], c["D"], seed=702)
+    ref = ho.head_forward(mid, attn, attn_cls, vocab, schema, gnn, ho.HEAD_CFG)
+    sn, m = build_modules(schema=schema, gnn=gnn, M=c["M"], K=c["K"], Vc=c["Vc"], D=c["D"])
+    out = SchemaHead(vocab.cuda(), sn, m)(mid.cuda(), attn.cuda(), attn_cls.cuda())
+    assert torch.equal(out["ingredients"].cpu(), ref["ingredients"])
+    rel_close(out["pred"], ref["pred"], what=f"{name} logits")
+    rel_close(out["feat_class"], ho.gnn_forward(gnn, ref["class_vertices"], ref["class_edges"], ref["class_ingredients"]),
+              what=f"{name} class embeddings")
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE configs[1]: B=256, d=384, M=1024) -- no oracle needed
 # ----------------------------------------------------------------------------------------------------------------
