@@ -192,6 +192,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     native.lib()
     c, vocab, sets, schema, gnn = make_problem(WORKLOAD, 1234 + rank, dev)

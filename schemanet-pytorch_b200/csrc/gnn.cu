@@ -249,7 +249,10 @@ pool_fc_kernel(const float *__restrict__ partial, int chunks, int D, int n_fixed
         pooled[d] = t / div;
     }
     __syncthreads();
-    for (int o = warp; o < D; o += (int)(blockDim.x >> 5)) {
+    // blockIdx.y splits the output features so that small batches still fill the machine
+    const int per = (D + gridDim.y - 1) / gridDim.y;
+    const int o_end = min(D, (int)(blockIdx.y + 1) * per);
+    for (int o = blockIdx.y * per + warp; o < o_end; o += (int)(blockDim.x >> 5)) {
         const float *w = fc_w + (size_t)o * D;
         float acc = 0.0f;
         for (int d = lane; d < D; d += kWarp) acc = fmaf(pooled[d], w[d], acc);
@@ -267,7 +270,7 @@ static int launch_pool_fc(const sh_gnn_params *p, const float *partial, int G, i
 {
     const int D = p->embed_dim;
     SH_LAUNCH("gnn_pool_fc", st,
-              pool_fc_kernel<<<G, 256, (size_t)D * sizeof(float), st>>>(partial, chunks, D, n_fixed, mean_div, p->fc_w, p->fc_b, out));
+              pool_fc_kernel<<<dim3(G, G >= 1024 ? 1 : 8), 256, (size_t)D * sizeof(float), st>>>(partial, chunks, D, n_fixed, mean_div, p->fc_w, p->fc_b, out));
     SH_CHECK_LAUNCH();
     return 0;
 }

@@ -1,0 +1,61 @@
+"""GPU, world_size 2, NCCL: class-sharded head (one all-gather of the class embeddings) and
+batch sharding.  Needs 2 GPUs: skipped on a single-GPU box (the gloo version of the plumbing runs on CPU)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (os.path.join(root, "schemanet-pytorch_b200"), os.path.join(root, "oracle"), os.path.join(root, "tests")):
+        sys.path.insert(0, p)
+    import head_oracle as ho
+    from schemanet_b200.head import SchemaHead
+    from schemanet_b200 import dist as shdist
+    from test_gpu_parity import build_modules
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        B, d, M, K, Vc, D = 10, 64, 128, 7, 128, 256          # K = 7 does not divide by 2: ragged class shards
+        vocab, mid, attn, attn_cls = ho.synth_inputs(B, d, M, seed=900)
+        schema = ho.synth_schema(M, K, Vc, seed=901)
+        gnn = ho.synth_gnn(M, D, seed=902)
+        sn, m = build_modules(schema=schema, gnn=gnn, M=M, K=K, Vc=Vc, D=D, dev=dev)
+        lo, hi = shdist.shard_range(B, rank, world)          # batch shard of this rank
+        mid_s, attn_s, cls_s = mid[:, lo:hi].contiguous().to(dev), attn[lo:hi].to(dev), attn_cls[lo:hi].to(dev)
+        full = SchemaHead(vocab.to(dev), sn, m)(mid_s, attn_s, cls_s)
+        shard = SchemaHead(vocab.to(dev), sn, m, class_shard=(rank, world))(mid_s, attn_s, cls_s)
+        assert torch.equal(shard["feat_class"], full["feat_class"]), "class embeddings differ under class sharding"
+        assert torch.equal(shard["pred"], full["pred"])
+        ref = ho.head_forward(mid[:, lo:hi].contiguous(), attn[lo:hi], attn_cls[lo:hi], vocab, schema, gnn, ho.HEAD_CFG)
+        err = (shard["pred"].cpu() - ref["pred"]).abs().max() / ref["pred"].abs().max()
+        assert err < 1e-5, f"rank {rank}: logits rel err {err:.2e}"
+        mv = shard["graphs"].max_vertices.clone()
+        shdist.global_max_vertices(mv)
+        sizes = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
+        dist.all_gather(sizes, shard["graphs"].max_vertices)
+        assert int(mv) == max(int(s) for s in sizes)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_class_sharded_head_world2_nccl():
+    mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)
