@@ -328,7 +328,7 @@ def run_gpu_arm(args):
             t = kern["class_edges_kernel"]["ms_per_launch"] * 1e-3
             stages["atlas"] = {"ms": t * 1e3, "GBps": alg["atlas"]["bytes"] / t / 1e9,
                                "frac_hbm": alg["atlas"]["bytes"] / t / 1e9 / hbm}
-        for name in ("discretize_exact_kernel", "discretize_tc_kernel"):
+        for name in ("discretize_exact_kernel", "discretize_tc_kernel", "discretize_tc_bf16_kernel"):
             if name in kern:
                 t = kern[name]["ms_per_launch"] * 1e-3
                 stages["discretize"] = {"ms": t * 1e3, "TFLOPs": alg["discretize"]["flops"] / t / 1e12, "kernel": name}

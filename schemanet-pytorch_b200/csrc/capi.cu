@@ -146,8 +146,7 @@ extern "C" int sh_device_info(int *sms, int *cc_major, int *cc_minor)
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" size_t sh_discretize_workspace_bytes(int64_t R, int d, int M)
 {
-    (void)d;
-    return carve_disc_workspace(nullptr, R, M).bytes;
+    return carve_disc_workspace(nullptr, R, M, d).bytes;
 }
 
 extern "C" int sh_dev_discretize(const float *tokens, const float *vocab, int64_t R, int d, int M, int64_t *out_idx,
@@ -157,18 +156,21 @@ extern "C" int sh_dev_discretize(const float *tokens, const float *vocab, int64_
     SH_REQUIRE(R > 0 && d > 0 && M > 0 && idx_rows > 0, "discretize: bad shape R=%lld d=%d M=%d", (long long)R, d, M);
     SH_REQUIRE(workspace && workspace_bytes >= sh_discretize_workspace_bytes(R, d, M), "discretize: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    DiscWorkspace ws = carve_disc_workspace(workspace, R, M);
-    bool tensor = false;
-    if (mode == SH_DISC_TENSOR) {
-        SH_REQUIRE(discretize_tc_supported(R, d, M), "discretize: tensor-core path needs d %% 32 == 0, M %% 16 == 0 (d=%d M=%d)", d, M);
+    DiscWorkspace ws = carve_disc_workspace(workspace, R, M, d);
+    bool tensor = false, bf16 = false;
+    if (mode == SH_DISC_TENSOR || mode == SH_DISC_TENSOR_BF16) {
+        bf16 = mode == SH_DISC_TENSOR_BF16;
+        SH_REQUIRE(discretize_tc_supported(R, d, M, bf16), "discretize: tensor-core path needs d %% %d == 0, d >= 32, M >= 16 (d=%d M=%d)",
+                   bf16 ? 8 : 4, d, M);
         tensor = true;
     } else if (mode == SH_DISC_AUTO) {
-        tensor = discretize_tc_supported(R, d, M);
+        bf16 = discretize_tc_supported(R, d, M, true);
+        tensor = bf16 || discretize_tc_supported(R, d, M, false);
     }
     SH_CHECK_CUDA(cudaMemsetAsync(ws.counters, 0, 256, st));
     if (launch_codebook_norms(vocab, M, d, ws, st)) return 1;
     if (tensor) {
-        if (launch_discretize_tc(tokens, vocab, R, d, M, out_idx, idx_rows, idx_row_stride, idx_col_stride, ws, st)) return 1;
+        if (launch_discretize_tc(tokens, vocab, R, d, M, out_idx, idx_rows, idx_row_stride, idx_col_stride, ws, bf16, st)) return 1;
     } else {
         if (launch_discretize_exact(tokens, vocab, ws.cn, R, d, M, out_idx, idx_rows, idx_row_stride, idx_col_stride, st)) return 1;
     }

@@ -20,12 +20,14 @@ struct DiscWorkspace {
     float *xn;                      // [R]  |x_r|^2
     int *cand_count;                // [R]
     int *cand_idx;                  // [R, kCandSlots]
+    unsigned short *xb;             // [R, d]  tokens rounded to bf16 (bf16 tensor-core path)
+    unsigned short *cb;             // [M, d]  codebook rounded to bf16
     size_t bytes;
 };
 
 inline size_t ws_align(size_t x) { return (x + 255) / 256 * 256; }
 
-inline DiscWorkspace carve_disc_workspace(void *base, int64_t R, int M)
+inline DiscWorkspace carve_disc_workspace(void *base, int64_t R, int M, int d)
 {
     DiscWorkspace w{};
     char *p = (char *)base;
@@ -35,6 +37,8 @@ inline DiscWorkspace carve_disc_workspace(void *base, int64_t R, int M)
     w.xn = (float *)(p + off); off += ws_align(sizeof(float) * (size_t)R);
     w.cand_count = (int *)(p + off); off += ws_align(sizeof(int) * (size_t)R);
     w.cand_idx = (int *)(p + off); off += ws_align(sizeof(int) * (size_t)R * kCandSlots);
+    w.xb = (unsigned short *)(p + off); off += ws_align(sizeof(unsigned short) * (size_t)R * d);
+    w.cb = (unsigned short *)(p + off); off += ws_align(sizeof(unsigned short) * (size_t)M * d);
     w.bytes = off;
     return w;
 }
@@ -47,8 +51,8 @@ int launch_gather(const float *vocab, const int64_t *idx, int64_t idx_rows, int6
 int launch_discretize_exact(const float *X, const float *C, const float *cn, int64_t R, int d, int M, int64_t *out_idx,
                             int64_t idx_rows, int64_t idx_row_stride, int64_t idx_col_stride, cudaStream_t st);
 // tensor-core path (discretize_tc.cu); returns -1 if the shape is not supported by it
-bool discretize_tc_supported(int64_t R, int d, int M);
+bool discretize_tc_supported(int64_t R, int d, int M, bool bf16);
 int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M, int64_t *out_idx, int64_t idx_rows,
-                         int64_t idx_row_stride, int64_t idx_col_stride, const DiscWorkspace &ws, cudaStream_t st);
+                         int64_t idx_row_stride, int64_t idx_col_stride, const DiscWorkspace &ws, bool bf16, cudaStream_t st);
 
 }  // namespace sh

@@ -15,6 +15,9 @@
 //   warp 0: TMA producer      warp 1: TMEM allocator + MMA issuer (one elected lane)      warps 2-5: epilogue
 // Pipelines: a 4-stage shared-memory ring (full/empty mbarriers, slots freed by tcgen05.commit) and a 2-stage TMEM
 // accumulator ring (tmem_full/tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
 #include "discretize.cuh"
 #include "tc_common.cuh"
 
@@ -27,6 +30,7 @@ constexpr int TC_BK = 32;        // fp32 per k-block = one 128-byte swizzle row
 constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 192;
 constexpr int kOverflowMark = -1;
+constexpr int kCandStride = kCandSlots + 1;   // slot kCandSlots absorbs the stores of a full list
 
 struct DiscTcArgs {
     int64_t R;
@@ -36,6 +40,7 @@ struct DiscTcArgs {
     const float *xn;       // [R]
     const unsigned *cmax_bits;   // bit pattern of max_j |c_j|^2
     float beta;
+    int debug;             // bit 0: epilogue skips its compute, bit 1: MMA issuer skips the MMAs (timing experiments)
     int64_t *out_idx;
     int64_t idx_rows, idx_row_stride, idx_col_stride;
     int *cand_count;       // [R]
@@ -49,13 +54,17 @@ struct DiscTcSmem {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = TC_STAGES * kStageBytes;
     static constexpr int kCandOffset = kBarOffset + 256;
-    static constexpr int kTotal = kCandOffset + TC_BM * kCandSlots * 8 + 1024;   // + slack for 1024-B alignment
+    static constexpr int kTotal = kCandOffset + TC_BM * kCandStride * 8 + 1024;   // + slack for 1024-B alignment
 };
 
-template <int BN>
+// kBf16: operands are bf16 copies (64 elements per 128-byte swizzle row, kind::f16, UMMA K = 16) instead of the fp32
+// tensors themselves (32 elements per row, kind::tf32, UMMA K = 8).  Same tile bytes and MMA count per k-block; half the
+// k-blocks, i.e. half the L2->SM operand traffic this kernel is bound by, at twice the tensor rate.
+template <int BN, bool kBf16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DiscTcArgs a)
 {
+    constexpr int KB_ELEMS = kBf16 ? 64 : 32;      // elements per k-block (one 128-byte row)
     using S = DiscTcSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -65,7 +74,7 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 2);
     float *cand_s = (float *)(smem + S::kCandOffset);
-    int *cand_i = (int *)(cand_s + TC_BM * kCandSlots);
+    int *cand_i = (int *)(cand_s + TC_BM * kCandStride);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -93,14 +102,14 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t *sa = smem + stage * S::kStageBytes;
                         mbar_arrive_expect_tx(&full[stage], S::kStageBytes);
-                        tma_load_2d(sa, &tmA, &full[stage], kb * TC_BK, mb * TC_BM);
-                        tma_load_2d(sa + S::kABytes, &tmB, &full[stage], kb * TC_BK, nb * BN);
+                        tma_load_2d(sa, &tmA, &full[stage], kb * KB_ELEMS, mb * TC_BM);
+                        tma_load_2d(sa + S::kABytes, &tmB, &full[stage], kb * KB_ELEMS, nb * BN);
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+        constexpr uint32_t idesc = kBf16 ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN);
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
         for (int mb = blockIdx.x; mb < a.num_m_blocks; mb += gridDim.x)
@@ -115,8 +124,10 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
                         const uint64_t da = make_desc_k_sw128(sa), db = make_desc_k_sw128(sa + S::kABytes);
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 8; ++k)   // UMMA K = 8 for tf32 = 32 bytes along the swizzle row
-                            umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        for (int k = 0; k < ((a.debug & 2) ? 0 : 4); ++k) {   // one UMMA consumes 32 bytes of K (8 tf32 / 16 bf16) of the 128-byte row
+                            if (kBf16) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                            else umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        }
                         umma_commit(&empty[stage]);          // slot is free once these MMAs have read it
                         if (kb == a.num_k_blocks - 1) umma_commit(&tmem_full[as]);
                     }
@@ -129,18 +140,17 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ===================== epilogue: fused score + running argmin + near-tie candidates =====================
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access
         const int row_in_tile = wq * 32 + lane;
-        float *my_s = cand_s + row_in_tile * kCandSlots;
-        int *my_i = cand_i + row_in_tile * kCandSlots;
+        float *my_s = cand_s + row_in_tile * kCandStride;
+        int *my_i = cand_i + row_in_tile * kCandStride;
         const float cmax = sqrtf(__uint_as_float(*a.cmax_bits));
         int as = 0;
         uint32_t aphase = 0;
         for (int mb = blockIdx.x; mb < a.num_m_blocks; mb += gridDim.x) {
             const int64_t row = (int64_t)mb * TC_BM + row_in_tile;
             const bool valid = row < a.R;
-            const float band = valid ? a.beta * 9.765625e-4f * sqrtf(a.xn[row]) * cmax : 0.0f;
+            const float band = valid ? a.beta * (kBf16 ? 3.90625e-3f : 9.765625e-4f) * sqrtf(a.xn[row]) * cmax : 0.0f;
             float m_run = INFINITY;
-            int cnt = 0;
-            bool overflow = false;
+            int cnt = 0;                  // candidates stored; kCandSlots means "full: some may have been lost"
             for (int nb = 0; nb < a.num_n_blocks; ++nb) {
                 mbar_wait(&tmem_full[as], aphase);
                 tc_fence_after();
@@ -148,7 +158,7 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     const int n_base = nb * BN + c * 32;
-                    if (n_base >= a.M) break;
+                    if (n_base >= a.M || (a.debug & 1)) break;
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
                     const float4 *cn4 = reinterpret_cast<const float4 *>(a.cn + n_base);
@@ -162,21 +172,18 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         v[4 * q + 3] = fmaf(-2.0f, v[4 * q + 3], cc.w);
                         cmin = fminf(cmin, fminf(fminf(v[4 * q], v[4 * q + 1]), fminf(v[4 * q + 2], v[4 * q + 3])));
                     }
+                    // A chunk matters to a row only if its minimum comes within `band` of the row's running minimum
+                    // (~ln(#chunks) times per row, but with 32 rows per warp some lane hits on most chunks, so this
+                    // path must stay short: straight-line, branch-free appends from the registers already loaded).
                     if (cmin <= m_run + band) {
+                        if (cmin < m_run - band) cnt = 0;          // every older candidate is now out of reach
                         m_run = fminf(m_run, cmin);
                         const float thr = m_run + band;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            if (v[j] <= thr && !overflow) {
-                                if (cnt == kCandSlots) {       // compact: drop entries the new minimum has ruled out
-                                    int keep = 0;
-                                    for (int t = 0; t < kCandSlots; ++t)
-                                        if (my_s[t] <= thr) { my_s[keep] = my_s[t]; my_i[keep] = my_i[t]; ++keep; }
-                                    cnt = keep;
-                                }
-                                if (cnt < kCandSlots) { my_s[cnt] = v[j]; my_i[cnt] = n_base + j; ++cnt; }
-                                else overflow = true;
-                            }
+                            my_s[cnt] = v[j];                       // unconditional store, conditional advance
+                            my_i[cnt] = n_base + j;
+                            cnt = min(cnt + ((v[j] <= thr) ? 1 : 0), kCandSlots);   // == kCandSlots: list is full
                         }
                     }
                 }
@@ -187,6 +194,7 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
             if (valid) {
                 const float thr = m_run + band;
+                const bool overflow = cnt >= kCandSlots;   // a full list may have dropped a candidate: exact rescan
                 int keep = 0, first = 0;
                 if (!overflow)
                     for (int t = 0; t < cnt; ++t)
@@ -255,10 +263,31 @@ codebook_norms_kernel(const float *__restrict__ C, int M, int padded, int d, flo
     }
 }
 
-bool discretize_tc_supported(int64_t R, int d, int M)
+// fp32 rows -> bf16 copy (round to nearest even) + |row|^2 of the ORIGINAL fp32 row, one warp per row
+__global__ void __launch_bounds__(256)
+rows_to_bf16_kernel(const float *__restrict__ x, int64_t rows, int d, unsigned short *__restrict__ xb, float *__restrict__ norm)
+{
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+        const float2 *p = reinterpret_cast<const float2 *>(x + r * d);
+        unsigned *q = reinterpret_cast<unsigned *>(xb + r * d);
+        float s = 0.0f;
+        for (int k = lane; k < d / 2; k += kWarp) {
+            const float2 v = p[k];
+            s = fmaf(v.x, v.x, s);
+            s = fmaf(v.y, v.y, s);
+            const unsigned lo = __bfloat16_as_ushort(__float2bfloat16_rn(v.x)), hi = __bfloat16_as_ushort(__float2bfloat16_rn(v.y));
+            q[k] = lo | (hi << 16);
+        }
+        s = warp_sum(s);
+        if (lane == 0 && norm) norm[r] = s;
+    }
+}
+
+bool discretize_tc_supported(int64_t R, int d, int M, bool bf16)
 {
     // TMA needs 16-byte aligned row strides; tiny problems are not worth a tensor-core launch
-    return d % 4 == 0 && d >= 32 && M >= 16 && R >= 1 && encode_tiled_fn() != nullptr;
+    return d % (bf16 ? 8 : 4) == 0 && d >= 32 && M >= 16 && R >= 1 && encode_tiled_fn() != nullptr;
 }
 
 int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws, cudaStream_t st)
@@ -270,35 +299,63 @@ int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws,
     return 0;
 }
 
-template <int BN>
+template <int BN, bool kBf16>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const DiscTcArgs &a, cudaStream_t st)
 {
     using S = DiscTcSmem<BN>;
     static bool configured = false;
     if (!configured) {
-        SH_CHECK_CUDA(cudaFuncSetAttribute(discretize_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        SH_CHECK_CUDA(cudaFuncSetAttribute(discretize_tc_kernel<BN, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         configured = true;
     }
     const int grid = min(a.num_m_blocks, sm_count());
-    SH_LAUNCH("discretize_tc_kernel", st, discretize_tc_kernel<BN><<<grid, TC_THREADS, S::kTotal, st>>>(tmA, tmB, a));
+    SH_LAUNCH(kBf16 ? "discretize_tc_bf16_kernel" : "discretize_tc_kernel", st,
+              discretize_tc_kernel<BN, kBf16><<<grid, TC_THREADS, S::kTotal, st>>>(tmA, tmB, a));
     SH_CHECK_LAUNCH();
     return 0;
 }
 
+// bf16 row-major [rows, cols]: box {64 bf16 (128 B), box_rows}
+static int make_tmap_bf16(CUtensorMap *map, const unsigned short *base, uint64_t cols, uint64_t rows, uint32_t box_rows)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    SH_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<unsigned short *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SH_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r);
+    return 0;
+}
+
 int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M, int64_t *out_idx, int64_t idx_rows,
-                         int64_t idx_row_stride, int64_t idx_col_stride, const DiscWorkspace &ws, cudaStream_t st)
+                         int64_t idx_row_stride, int64_t idx_col_stride, const DiscWorkspace &ws, bool bf16, cudaStream_t st)
 {
     SH_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)C % 16 == 0), "discretize: tensor-core path needs 16-byte aligned inputs");
     const int BN = M > 128 ? 256 : (M > 64 ? 128 : 64);
     CUtensorMap tmA, tmB;
-    if (make_tmap_f32(&tmA, X, (uint64_t)d, (uint64_t)R, 1, (uint64_t)d, 0, TC_BM)) return 1;
-    if (make_tmap_f32(&tmB, C, (uint64_t)d, (uint64_t)M, 1, (uint64_t)d, 0, (uint32_t)BN)) return 1;
-    if (launch_row_sqnorm(X, R, d, ws.xn, st)) return 1;
+    if (bf16) {
+        // one pass over the tokens produces the bf16 copy and |x|^2 (the fp32 path needs that pass for |x|^2 anyway)
+        const int g1 = (int)min(ceil_div64(R, 8), (int64_t)sm_count() * 16), g2 = (int)min(ceil_div64(M, 8), (int64_t)sm_count() * 16);
+        SH_LAUNCH("rows_to_bf16_kernel", st, rows_to_bf16_kernel<<<g1, 256, 0, st>>>(X, R, d, ws.xb, ws.xn));
+        SH_CHECK_LAUNCH();
+        SH_LAUNCH("rows_to_bf16_kernel", st, rows_to_bf16_kernel<<<g2, 256, 0, st>>>(C, M, d, ws.cb, nullptr));
+        SH_CHECK_LAUNCH();
+        if (make_tmap_bf16(&tmA, ws.xb, (uint64_t)d, (uint64_t)R, TC_BM)) return 1;
+        if (make_tmap_bf16(&tmB, ws.cb, (uint64_t)d, (uint64_t)M, (uint32_t)BN)) return 1;
+    } else {
+        if (make_tmap_f32(&tmA, X, (uint64_t)d, (uint64_t)R, 1, (uint64_t)d, 0, TC_BM)) return 1;
+        if (make_tmap_f32(&tmB, C, (uint64_t)d, (uint64_t)M, 1, (uint64_t)d, 0, (uint32_t)BN)) return 1;
+        if (launch_row_sqnorm(X, R, d, ws.xn, st)) return 1;
+    }
     DiscTcArgs a{};
     a.R = R; a.d = d; a.M = M;
     a.num_m_blocks = (int)ceil_div64(R, TC_BM);
     a.num_n_blocks = ceil_div(M, BN);
-    a.num_k_blocks = ceil_div(d, TC_BK);
+    a.num_k_blocks = ceil_div(d, bf16 ? 64 : TC_BK);
     a.cn = ws.cn; a.xn = ws.xn; a.cmax_bits = (const unsigned *)(ws.counters + 2);
     // band = beta * 2^-10 * |x| * max|c|: >= 13 sigma of the tf32 truncation noise for i.i.d. data, and the rigorous
     // worst-case bound when beta reaches 8 ("tf32 band")
@@ -306,10 +363,17 @@ int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M
     a.beta = beta < 1.0f ? 1.0f : (beta > 8.0f ? 8.0f : beta);
     a.out_idx = out_idx; a.idx_rows = idx_rows; a.idx_row_stride = idx_row_stride; a.idx_col_stride = idx_col_stride;
     a.cand_count = ws.cand_count; a.cand_idx = ws.cand_idx;
+    { const char *e = getenv("SCHEMANET_DISC_DEBUG"); a.debug = e ? atoi(e) : 0; }
     int rc;
-    if (BN == 256) rc = launch_tc<256>(tmA, tmB, a, st);
-    else if (BN == 128) rc = launch_tc<128>(tmA, tmB, a, st);
-    else rc = launch_tc<64>(tmA, tmB, a, st);
+    if (bf16) {
+        if (BN == 256) rc = launch_tc<256, true>(tmA, tmB, a, st);
+        else if (BN == 128) rc = launch_tc<128, true>(tmA, tmB, a, st);
+        else rc = launch_tc<64, true>(tmA, tmB, a, st);
+    } else {
+        if (BN == 256) rc = launch_tc<256, false>(tmA, tmB, a, st);
+        else if (BN == 128) rc = launch_tc<128, false>(tmA, tmB, a, st);
+        else rc = launch_tc<64, false>(tmA, tmB, a, st);
+    }
     if (rc) return rc;
     const int grid = (int)min(ceil_div64(R, 8), (int64_t)sm_count() * 8);
     SH_LAUNCH("discretize_recheck_kernel", st,

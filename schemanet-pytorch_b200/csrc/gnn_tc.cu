@@ -18,6 +18,7 @@
 //                -> H^T [D, n] as hi/lo for the next layer's adj GEMM, or H [rows, D] for the pooling.
 // Kernel layout is the same as discretize_tc.cu: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5
 // epilogue; 2-stage 96 KB shared-memory ring, 2-stage 256-column TMEM accumulator ring.
+#include <stdlib.h>
 #include "common.cuh"
 #include "gnn_tc.cuh"
 #include "tc_common.cuh"
@@ -29,15 +30,8 @@ using namespace tc;
 constexpr int G_BM = 128;
 constexpr int G_BN = 256;      // == embed_dim
 constexpr int G_BK = 32;
-constexpr int G_STAGES = 2;
 constexpr int G_THREADS = 192;
 constexpr int kABytes = G_BM * G_BK * 4;                 // 16 KB
-constexpr int kBBytes = G_BN * G_BK * 4;                 // 32 KB
-constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // hi + lo of both operands: 96 KB
-constexpr int kBarOffset = G_STAGES * kStageBytes;
-constexpr int kParamOffset = kBarOffset + 256;              // bias / gamma / beta of the fused LayerNorm epilogue
-constexpr int kStageOutOffset = kParamOffset + 3 * G_BN * 4;   // per-epilogue-warp 32x33 fp32 transpose buffers
-constexpr int kSmemTotal = kStageOutOffset + 4 * 32 * 33 * 4 + 1024;
 
 enum { EPI_STORE_SPLIT = 0, EPI_LN_RELU_T_SPLIT = 1, EPI_LN_RELU_ROWS = 2 };
 
@@ -96,52 +90,75 @@ __device__ __forceinline__ void store_chunk_rows(float *tile /* [32][33] */, con
     }
 }
 
-template <int EPI>
+// Shared-memory plan.  CTAS == 1: one CTA per 128-row block, stage = hi+lo of A (2 x 16 KB) and of the whole 256-row
+// B tile (2 x 32 KB) = 96 KB, 2 stages.  CTAS == 2 (cta_group::2): a CTA pair computes a 256-row block with one UMMA
+// of M = 256; each CTA stages its own 128 A rows and HALF of the B tile (2 x 16 KB), i.e. 64 KB per stage and a third
+// less L2->SM traffic per flop, which buys a third stage.
+template <int CTAS>
+struct GemmPlan {
+    static constexpr int kBRows = G_BN / CTAS;
+    static constexpr int kBBytesL = kBRows * G_BK * 4;
+    static constexpr int kStage = 2 * kABytes + 2 * kBBytesL;
+    static constexpr int kStages = CTAS == 1 ? 2 : 3;
+    static constexpr int kBar = kStages * kStage;
+    static constexpr int kParam = kBar + 256;
+    static constexpr int kStageOut = kParam + 3 * G_BN * 4;
+    static constexpr int kTotal = kStageOut + 4 * 32 * 33 * 4 + 1024;
+};
+
+template <int EPI, int CTAS>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, GemmTcArgs a)
 {
+    using P = GemmPlan<CTAS>;
+    constexpr int S = P::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = (uint64_t *)(smem + kBarOffset);
-    uint64_t *empty = full + G_STAGES;
-    uint64_t *tmem_full = empty + G_STAGES;
+    uint64_t *full = (uint64_t *)(smem + P::kBar);
+    uint64_t *empty = full + S;
+    uint64_t *tmem_full = empty + S;
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 2);
-    float *s_bias = (float *)(smem + kParamOffset), *s_gamma = s_bias + G_BN, *s_beta = s_gamma + G_BN;
-    float *s_out = (float *)(smem + kStageOutOffset);
+    float *s_bias = (float *)(smem + P::kParam), *s_gamma = s_bias + G_BN, *s_beta = s_gamma + G_BN;
+    float *s_out = (float *)(smem + P::kStageOut);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;     // 0 = the CTA that issues the MMAs
+    const int unit = (int)blockIdx.x / CTAS, num_units = (int)gridDim.x / CTAS;
 
     if (EPI != EPI_STORE_SPLIT)
         for (int i = threadIdx.x; i < G_BN; i += G_THREADS) { s_bias[i] = a.bias[i]; s_gamma[i] = a.gamma[i]; s_beta[i] = a.beta[i]; }
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
-        for (int s = 0; s < G_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * CTAS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, 2 * G_BN);
+    if (CTAS == 2) cluster_sync();       // the peer's barriers must exist before anything signals them
+    if (warp == 1) { if (CTAS == 2) tmem_alloc_pair(tmem_ptr, 2 * G_BN); else tmem_alloc(tmem_ptr, 2 * G_BN); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int mb_per = ceil_div(a.M_total, G_BM);
-    const int tiles = a.G * mb_per;
+    constexpr int UB = G_BM * CTAS;                      // rows per work unit (a CTA, or a CTA pair)
+    const int ub_per = ceil_div(a.M_total, UB);
+    const int tiles = a.G * ub_per;
 
-    // every role walks the same tile list and applies the same skip rule
+    // every role of every CTA walks the same unit list and applies the same skip rule
 #define TILE_LOOP_BEGIN                                                                                   \
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {                                                 \
-        const int g = t / mb_per, mb = t % mb_per;                                                        \
+    for (int t = unit; t < tiles; t += num_units) {                                                       \
+        const int g = t / ub_per, ub = t % ub_per;                                                        \
+        const int mb = ub * CTAS + rank;   /* this CTA's 128-row block */                                 \
         const int n_g = (a.k_sizes && a.G > 1) ? a.k_sizes[g] : a.K_total;                                \
-        if (a.G > 1 && !a.identity_tail && mb * G_BM >= n_g) continue;                                    \
-        /* k-blocks [0, kA) cover the active range; with identity_tail a row block that holds rows >= n_g  \
+        if (a.G > 1 && !a.identity_tail && ub * UB >= n_g) continue;                                      \
+        /* k-blocks [0, kA) cover the active range; with identity_tail a unit that holds rows >= n_g       \
            additionally visits the k-blocks of its own diagonal that are not in [0, kA) */                 \
-        const int kA = (a.G > 1 && a.identity_tail && mb * G_BM >= n_g) ? 0 : ceil_div(n_g, G_BK);         \
+        const int kA = (a.G > 1 && a.identity_tail && ub * UB >= n_g) ? 0 : ceil_div(n_g, G_BK);           \
         int k2s = 0, k2c = 0;                                                                             \
-        if (a.identity_tail && (mb + 1) * G_BM > n_g) {                                                   \
-            k2s = max(kA, mb * (G_BM / G_BK));                                                            \
-            k2c = max(0, min((mb + 1) * (G_BM / G_BK), ceil_div(a.K_total, G_BK)) - k2s);                  \
+        if (a.identity_tail && (ub + 1) * UB > n_g) {                                                     \
+            k2s = max(kA, ub * (UB / G_BK));                                                              \
+            k2c = max(0, min((ub + 1) * (UB / G_BK), ceil_div(a.K_total, G_BK)) - k2s);                    \
         }                                                                                                 \
         const int kblocks = kA + k2c;                                                                     \
         if (kblocks == 0) continue;
@@ -155,46 +172,70 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                 for (int kidx = 0; kidx < kblocks; ++kidx) {
                     const int kb = kidx < kA ? kidx : k2s + (kidx - kA);
                     mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t *s = smem + stage * kStageBytes;
-                    mbar_arrive_expect_tx(&full[stage], kStageBytes);
-                    tma_load_3d(s, &tmAh, &full[stage], kb * G_BK, mb * G_BM, g);
-                    tma_load_3d(s + kABytes, &tmAl, &full[stage], kb * G_BK, mb * G_BM, g);
-                    tma_load_3d(s + 2 * kABytes, &tmBh, &full[stage], kb * G_BK, 0, a.batched_b ? g : 0);
-                    tma_load_3d(s + 2 * kABytes + kBBytes, &tmBl, &full[stage], kb * G_BK, 0, a.batched_b ? g : 0);
-                    if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+                    uint8_t *s = smem + stage * P::kStage;
+                    const int gb = a.batched_b ? g : 0;
+                    if (CTAS == 1) {
+                        mbar_arrive_expect_tx(&full[stage], P::kStage);
+                        tma_load_3d(s, &tmAh, &full[stage], kb * G_BK, mb * G_BM, g);
+                        tma_load_3d(s + kABytes, &tmAl, &full[stage], kb * G_BK, mb * G_BM, g);
+                        tma_load_3d(s + 2 * kABytes, &tmBh, &full[stage], kb * G_BK, 0, gb);
+                        tma_load_3d(s + 2 * kABytes + P::kBBytesL, &tmBl, &full[stage], kb * G_BK, 0, gb);
+                    } else {
+                        // both CTAs' bytes complete on the LEADER's barrier (the only one the MMA issuer waits on)
+                        const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * P::kStage);
+                        tma_load_3d_pair(s, &tmAh, lead_full, kb * G_BK, mb * G_BM, g);
+                        tma_load_3d_pair(s + kABytes, &tmAl, lead_full, kb * G_BK, mb * G_BM, g);
+                        tma_load_3d_pair(s + 2 * kABytes, &tmBh, lead_full, kb * G_BK, rank * P::kBRows, gb);
+                        tma_load_3d_pair(s + 2 * kABytes + P::kBBytesL, &tmBl, lead_full, kb * G_BK, rank * P::kBRows, gb);
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             TILE_LOOP_END
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_tf32(G_BM, G_BN);
-        int stage = 0, as = 0;
-        uint32_t phase = 0, aphase = 0;
-        TILE_LOOP_BEGIN
-            mbar_wait(&tmem_empty[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(as * G_BN);
-            for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait(&full[stage], phase);
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(G_BM * CTAS, G_BN);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            TILE_LOOP_BEGIN
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t s = smem_u32(smem + stage * kStageBytes);
-                    const uint64_t ah = make_desc_k_sw128(s), al = make_desc_k_sw128(s + kABytes);
-                    const uint64_t bh = make_desc_k_sw128(s + 2 * kABytes), bl = make_desc_k_sw128(s + 2 * kABytes + kBBytes);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * G_BN);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t s = smem_u32(smem + stage * P::kStage);
+                        const uint64_t ah = make_desc_k_sw128(s), al = make_desc_k_sw128(s + kABytes);
+                        const uint64_t bh = make_desc_k_sw128(s + 2 * kABytes), bl = make_desc_k_sw128(s + 2 * kABytes + P::kBBytesL);
 #pragma unroll
-                    for (int k = 0; k < G_BK / 8; ++k) {
-                        const uint64_t o = (uint64_t)(2 * k);
-                        umma_tf32(tmem_d, al + o, bh + o, idesc, (kb | k) != 0);   // small terms first
-                        umma_tf32(tmem_d, ah + o, bl + o, idesc, 1);
-                        umma_tf32(tmem_d, ah + o, bh + o, idesc, 1);
+                        for (int k = 0; k < G_BK / 8; ++k) {
+                            const uint64_t o = (uint64_t)(2 * k);
+                            if (CTAS == 1) {
+                                umma_tf32(tmem_d, al + o, bh + o, idesc, (kb | k) != 0);   // small terms first
+                                umma_tf32(tmem_d, ah + o, bl + o, idesc, 1);
+                                umma_tf32(tmem_d, ah + o, bh + o, idesc, 1);
+                            } else {
+                                umma_tf32_pair(tmem_d, al + o, bh + o, idesc, (kb | k) != 0);
+                                umma_tf32_pair(tmem_d, ah + o, bl + o, idesc, 1);
+                                umma_tf32_pair(tmem_d, ah + o, bh + o, idesc, 1);
+                            }
+                        }
+                        if (CTAS == 1) {
+                            umma_commit(&empty[stage]);
+                            if (kb == kblocks - 1) umma_commit(&tmem_full[as]);
+                        } else {
+                            umma_commit_pair(&empty[stage], 3);                    // frees the slot in both CTAs
+                            if (kb == kblocks - 1) umma_commit_pair(&tmem_full[as], 3);
+                        }
                     }
-                    umma_commit(&empty[stage]);
-                    if (kb == kblocks - 1) umma_commit(&tmem_full[as]);
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
-            }
-            if (++as == 2) { as = 0; aphase ^= 1; }
-        TILE_LOOP_END
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            TILE_LOOP_END
+        }
     } else {
         const int wq = warp & 3;
         const int row_in_tile = wq * 32 + lane;
@@ -276,7 +317,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) {
+                if (CTAS == 1) mbar_arrive(&tmem_empty[as]);
+                else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));   // the leader owns the accumulator ring
+            }
             if (++as == 2) { as = 0; aphase ^= 1; }
         TILE_LOOP_END
     }
@@ -284,7 +328,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
 #undef TILE_LOOP_END
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * G_BN);
+    if (CTAS == 2) cluster_sync();       // the peer may still be reading this CTA's shared memory / signalling its barriers
+    if (warp == 1) { if (CTAS == 2) tmem_dealloc_pair(tmem_base, 2 * G_BN); else tmem_dealloc(tmem_base, 2 * G_BN); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -442,17 +487,18 @@ class_perm_kernel(const float *__restrict__ cv, const int64_t *__restrict__ ci, 
 // Compacted class adjacency as hi/lo.  Only the parts the GEMM reads are written: the active corner (plus its padding
 // up to the tile edges) and the 128x128 diagonal blocks of row blocks that contain inactive vertices.
 __global__ void __launch_bounds__(256)
-class_adj_prep_kernel(const float *__restrict__ ce, int Vc, int ldk, const int32_t *__restrict__ n_act,
+class_adj_prep_kernel(const float *__restrict__ ce, int Vc, int ldk, int unit_rows, const int32_t *__restrict__ n_act,
                       const int32_t *__restrict__ old_of_new, float *__restrict__ adj_hi, float *__restrict__ adj_lo)
 {
     __shared__ float tile[32][33];
     const int k = blockIdx.z;
     const int nA = n_act[k];
     const int pi0 = blockIdx.y * 32, pj0 = blockIdx.x * 32;
-    const int rowsA = min(Vc, (nA + G_BM - 1) / G_BM * G_BM), colsA = (nA + G_BK - 1) / G_BK * G_BK;
-    const int mb = pi0 / G_BM;
+    // unit_rows = rows one GEMM work unit covers (128 for a single CTA, 256 for a CTA pair): see TILE_LOOP in gemm3x_kernel
+    const int rowsA = min(Vc, (nA + unit_rows - 1) / unit_rows * unit_rows), colsA = (nA + G_BK - 1) / G_BK * G_BK;
+    const int ub = pi0 / unit_rows;
     const bool in_a = pi0 < rowsA && pj0 < colsA;
-    const bool in_b = (mb + 1) * G_BM > nA && pj0 / G_BM == mb;
+    const bool in_b = (ub + 1) * unit_rows > nA && pj0 / unit_rows == ub;
     if (!in_a && !in_b) return;
     const float *cek = ce + (size_t)k * Vc * Vc;
     const int32_t *old = old_of_new + (size_t)k * Vc;
@@ -529,19 +575,53 @@ size_t gnn_tc_workspace_bytes(int G, int n_fixed, int D, int chunks)
     return carve_tc(nullptr, G, n_fixed, D).bytes + 4096;
 }
 
-template <int EPI>
-static int launch_gemm3x(const CUtensorMap *maps, const GemmTcArgs &a, const char *name, cudaStream_t st)
+static int gemm_ctas()
 {
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("SCHEMANET_GEMM_CTAS");
+        v = (e && e[0] == '1') ? 1 : 2;
+    }
+    return v;
+}
+
+template <int EPI, int CTAS>
+static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const char *name, cudaStream_t st)
+{
+    using P = GemmPlan<CTAS>;
     static bool configured = false;
     if (!configured) {
-        SH_CHECK_CUDA(cudaFuncSetAttribute(gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+        SH_CHECK_CUDA(cudaFuncSetAttribute(gemm3x_kernel<EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kTotal));
         configured = true;
     }
-    const int tiles = a.G * ceil_div(a.M_total, G_BM);
-    const int grid = min(tiles, sm_count());
-    SH_LAUNCH(name, st, gemm3x_kernel<EPI><<<grid, G_THREADS, kSmemTotal, st>>>(maps[0], maps[1], maps[2], maps[3], a));
+    const int units = a.G * ceil_div(a.M_total, G_BM * CTAS);
+    const int num_units = min(units, sm_count() / CTAS);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(num_units * CTAS);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = P::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    prof_begin(name, st);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm3x_kernel<EPI, CTAS>, maps[0], maps[1], maps[2], maps[3], a);
+    prof_end(st);
+    if (e != cudaSuccess) { set_error("%s launch -> %s", name, cudaGetErrorString(e)); return 1; }
     SH_CHECK_LAUNCH();
     return 0;
+}
+
+// maps: {A hi, A lo, B hi, B lo} for one CTA per row block, maps2: the same with 128-row B boxes for CTA pairs
+template <int EPI>
+static int launch_gemm3x(const CUtensorMap *maps, const CUtensorMap *maps2, const GemmTcArgs &a, const char *name, cudaStream_t st)
+{
+    if (gemm_ctas() == 2) return launch_gemm3x_n<EPI, 2>(maps2, a, name, st);
+    return launch_gemm3x_n<EPI, 1>(maps, a, name, st);
 }
 
 // 3-D map over [batch, rows, cols]; a batch of 1 still uses rank 3 so that the kernel issues one kind of TMA
@@ -582,6 +662,11 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     if (tmap3(&ym[1], b.y_lo, D, (uint64_t)G * n_fixed, 1, D, 0, G_BM)) return 1;
     if (tmap3(&wm[0], b.w_hi, D, D, 1, D, 0, G_BN)) return 1;
     if (tmap3(&wm[1], b.w_lo, D, D, 1, D, 0, G_BN)) return 1;
+    CUtensorMap xtm2[2], wm2[2];      // CTA pairs stage half of the B tile each
+    if (tmap3(&xtm2[0], b.xt_hi, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN / 2)) return 1;
+    if (tmap3(&xtm2[1], b.xt_lo, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN / 2)) return 1;
+    if (tmap3(&wm2[0], b.w_hi, D, D, 1, D, 0, G_BN / 2)) return 1;
+    if (tmap3(&wm2[1], b.w_lo, D, D, 1, D, 0, G_BN / 2)) return 1;
 
     for (int l = 0; l < p->num_layers; ++l) {
         const bool last = (l == p->num_layers - 1);
@@ -593,15 +678,17 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
         a.k_sizes = k_sizes; a.identity_tail = identity_tail; a.batched_b = 1;
         a.out_hi = b.y_hi; a.out_lo = b.y_lo;
         CUtensorMap m1[4] = {adjm[0], adjm[1], xtm[0], xtm[1]};
-        if (launch_gemm3x<EPI_STORE_SPLIT>(m1, a, "gnn_adj_gemm_tc", st)) return 1;
+        CUtensorMap m1p[4] = {adjm[0], adjm[1], xtm2[0], xtm2[1]};
+        if (launch_gemm3x<EPI_STORE_SPLIT>(m1, m1p, a, "gnn_adj_gemm_tc", st)) return 1;
         // H = relu(LN(Y W^T + b))
         GemmTcArgs c{};
         c.G = 1; c.rows_per_graph = n_fixed; c.M_total = G * n_fixed; c.K_total = D; c.row_sizes = row_sizes; c.batched_b = 0;
         c.bias = p->lin_b[l]; c.gamma = p->ln_w[l]; c.beta = p->ln_b[l]; c.eps = p->ln_eps;
         c.out_hi = b.xt_hi; c.out_lo = b.xt_lo; c.ldk = ldk; c.out_rows = b.h_rows;
         CUtensorMap m2[4] = {ym[0], ym[1], wm[0], wm[1]};
-        if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m2, c, "gnn_linear_ln_tc", st)) return 1; }
-        else { if (launch_gemm3x<EPI_LN_RELU_T_SPLIT>(m2, c, "gnn_linear_ln_tc", st)) return 1; }
+        CUtensorMap m2p[4] = {ym[0], ym[1], wm2[0], wm2[1]};
+        if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
+        else { if (launch_gemm3x<EPI_LN_RELU_T_SPLIT>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
     }
     dim3 grid(chunks, G);
     SH_LAUNCH("gnn_pool_rows", st, pool_rows_kernel<<<grid, 256, 0, st>>>(b.h_rows, vertex_w, ld_v, row_sizes, n_fixed, D, chunks, partial));
@@ -634,7 +721,7 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
     SH_CHECK_LAUNCH();
     dim3 grid(ceil_div(b.ldk, 32), ceil_div(Vc, 32), K);
     SH_LAUNCH("class_adj_prep_kernel", st,
-              class_adj_prep_kernel<<<grid, 256, 0, st>>>(class_edges, Vc, b.ldk, b.n_act, b.old_of_new, b.adj_hi, b.adj_lo));
+              class_adj_prep_kernel<<<grid, 256, 0, st>>>(class_edges, Vc, b.ldk, G_BM * gemm_ctas(), b.n_act, b.old_of_new, b.adj_hi, b.adj_lo));
     SH_CHECK_LAUNCH();
     return run_layers_tc(p, K, Vc, b.n_act, 1, nullptr, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st);
 }

@@ -198,9 +198,10 @@ def test_discretize_vs_oracle(B, d, M, mode):
         assert len(bad) == 0
 
 
+@pytest.mark.parametrize("operands", ["tf32", "bf16"])
 @pytest.mark.parametrize("B,d,M,mode", [(64, 384, 1024, "hard"), (16, 768, 8000, "hard"), (64, 192, 128, "easy"),
                                         (7, 96, 200, "hard")])
-def test_discretize_tensor_core_vs_exact_path(B, d, M, mode):
+def test_discretize_tensor_core_vs_exact_path(B, d, M, mode, operands):
     """tcgen05 (tf32 coarse pass + fp32 re-check) against the fp32 CUDA-core scan on the same device: any
     difference must sit on an fp32-ambiguous row; the re-check statistics are reported."""
     from schemanet_b200 import native
@@ -208,10 +209,11 @@ def test_discretize_tensor_core_vs_exact_path(B, d, M, mode):
     flat = mid[1:].reshape(-1, d).cuda()
     v = vocab.cuda()
     exact = native.discretize(flat, v, mode=native.DISC_EXACT)
-    tens, ws = native.discretize(flat, v, mode=native.DISC_TENSOR, return_workspace=True)
+    tc_mode = native.DISC_TENSOR if operands == "tf32" else native.DISC_TENSOR_BF16
+    tens, ws = native.discretize(flat, v, mode=tc_mode, return_workspace=True)
     stats = native.discretize_stats(ws)
     bad = (exact != tens).nonzero().flatten().cpu()
-    print(f"tensor-core discretize B={B} d={d} M={M} {mode}: recheck rows {stats['recheck_rows']} / {flat.shape[0]}, "
+    print(f"tensor-core ({operands}) discretize B={B} d={d} M={M} {mode}: recheck rows {stats['recheck_rows']} / {flat.shape[0]}, "
           f"overflow rows {stats['overflow_rows']}, mismatches vs exact {len(bad)}")
     if len(bad):
         _, gap = ho.discretize_fp64_gap(flat.cpu()[bad], vocab)
@@ -227,7 +229,7 @@ def test_discretize_edge_cases():
     vocab[40:48] = vocab[8:16]                      # exact duplicates: the lower index must win
     x = torch.cat([vocab, vocab + 1e-4, torch.zeros(3, 40)])
     want = torch.cdist(x, vocab).argmin(1)
-    for mode in (native.DISC_AUTO, native.DISC_EXACT):
+    for mode in (native.DISC_AUTO, native.DISC_EXACT, native.DISC_TENSOR, native.DISC_TENSOR_BF16):
         got = native.discretize(x.cuda(), vocab.cuda(), mode=mode).cpu()
         assert torch.equal(got, want)
     assert bool((got[40:48] == torch.arange(8, 16)).all())
