@@ -164,7 +164,7 @@ def workload_config(c, n_gpus):
     return {"workload": "DeiT-Small SchemaNet head, CIFAR-100 shape (BASELINE.json configs[1])", "batch_per_gpu": c["B"],
             "global_batch": c["B"] * n_gpus, "tokens": L, "d": c["d"], "vocab_M": c["M"], "classes_K": c["K"],
             "class_vertices_Vc": c["Vc"], "gnn_dim_D": c["D"], "parallelism": f"batch-shard dp{n_gpus}",
-            "class_side": "recomputed every step (reference semantics)",
+            "class_side": "recomputed every step (reference semantics), on a second CUDA stream overlapping the instance side",
             "cache_policy": "3 rotating input sets (116 MB each) + 419 MB class edges streamed per step: larger than "
                             "the 126 MB L2"}
 
@@ -261,11 +261,15 @@ def run_gpu_arm(args):
         # per-kernel CUDA-event timings over a further K steps of the same workload (events on the launching stream)
         out = step(0)
         n_bar = float(out["graphs"].num_vertices.float().mean())
+        # per-kernel durations are taken with the class-side stream serialised behind the main stream, so that a
+        # kernel's time is its own (in the headline run above the two streams overlap)
+        head.overlap_class_side = False
         native.profile_enable(True)
         for i in range(args.steps):
             step(i)
         prof = native.profile_collect()
         native.profile_enable(False)
+        head.overlap_class_side = True
         peaks = load_peaks()
         alg = stage_bytes_flops(c, n_bar)
         kern = {k: {"launches": v[0], "ms_total": v[1], "ms_per_launch": v[1] / max(v[0], 1)} for k, v in prof.items()}

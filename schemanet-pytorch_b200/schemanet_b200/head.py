@@ -46,6 +46,13 @@ class SchemaHead:
         self.disc_mode = disc_mode
         self.ws = HeadWorkspace()
         self._class_cache = None
+        # The class side (atlas + class-graph GNN: mostly HBM-bound passes over [K, Vc, Vc]) does not depend on the
+        # batch, so it runs on its own stream and overlaps the tensor-core-bound instance side; joined before the logits.
+        self.overlap_class_side = True
+        self._class_stream = None
+        self._class_out = None
+        self._fork = None
+        self._join = None
 
     # -- stage 1 -------------------------------------------------------------------------------------------------
     def discretize(self, mid_feat: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
@@ -63,7 +70,14 @@ class SchemaHead:
         K = vw.shape[0]
         if self.class_shard is None:
             gnn._check_inference()
-            cv, ce, f_kg = native.class_side(gnn.param_pack(), vw, ew, ci, sn.prune_node_threshold, True, sn.remove_self_loop)
+            if self._class_out is None or self._class_out[1].shape != ew.shape or self._class_out[1].device != ew.device:
+                Vc = vw.shape[1]
+                self._class_out = (torch.empty(K, Vc, dtype=torch.float32, device=vw.device),
+                                   torch.empty(K, Vc, Vc, dtype=torch.float32, device=vw.device),
+                                   torch.empty(K, gnn.embed_dim, dtype=torch.float32, device=vw.device))
+            # persistent outputs: nothing is allocated per step (and nothing needs cross-stream allocator bookkeeping)
+            cv, ce, f_kg = native.class_side(gnn.param_pack(), vw, ew, ci, sn.prune_node_threshold, True, sn.remove_self_loop,
+                                             out=self._class_out)
             self.atlas = {"class_vertices": cv, "class_edges": ce, "class_ingredients": ci}
             return f_kg
         import torch.distributed as dist
@@ -100,12 +114,27 @@ class SchemaHead:
         native.instance_graphs(ingredients, attn, attn_cls, geo, sn.vertex_attribute_weights.tensor,
                                sn.edge_attribute_weights.tensor, sn.clamp_vertex_attn, sn.clamp_edge_attn,
                                raw_logits=True, heads=heads, mean=True, out=graphs)
+        side = None
         if cache_class and self._class_cache is not None:
             f_kg = self._class_cache
+        elif self.overlap_class_side and self.class_shard is None:
+            main = torch.cuda.current_stream(mid_feat.device)
+            if self._class_stream is None:
+                self._class_stream = torch.cuda.Stream(device=mid_feat.device)
+                self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
+            side = self._class_stream
+            self._fork.record(main)             # parameters written earlier on the main stream are visible to the side stream
+            side.wait_event(self._fork)
+            with torch.cuda.stream(side):
+                f_kg = self.class_features()
+                self._join.record(side)
+            self._class_cache = f_kg if cache_class else None
         else:
             f_kg = self.class_features()
             self._class_cache = f_kg if cache_class else None
         f_inst = self.matcher.gnn.forward_packed(graphs)
+        if side is not None:
+            torch.cuda.current_stream(mid_feat.device).wait_event(self._join)
         pred = native.similarity(f_inst, f_kg, self.matcher.similarity_name)
         return {"pred": pred, "ingredients": ingredients, "graphs": graphs, "feat_instance": f_inst, "feat_class": f_kg}
 

@@ -319,7 +319,7 @@ def gnn_forward(params, G, n_fixed, sizes, ids, vertex_w, ld_v, edges, edge_batc
 
 
 def class_side(params, vertex_weights, edge_weights, class_ingredients, prune_threshold=None, prune_in_place=True,
-               remove_self_loop=False):
+               remove_self_loop=False, out=None):
     """get_atlas() + GNN(class graphs) in one call -> (class_vertices, class_edges, feat_class [K, D])."""
     require_cuda(vertex_weights, edge_weights, class_ingredients)
     K, Vc = vertex_weights.shape
@@ -329,14 +329,17 @@ def class_side(params, vertex_weights, edge_weights, class_ingredients, prune_th
         raise RuntimeError("edge_weights must be a contiguous float32 CUDA tensor")
     ci = _i64c(class_ingredients)
     D = params.embed_dim
-    cv = torch.empty(K, Vc, dtype=torch.float32, device=vw.device)
-    ce = torch.empty(K, Vc, Vc, dtype=torch.float32, device=vw.device)
-    out = torch.empty(K, D, dtype=torch.float32, device=vw.device)
+    if out is None:
+        cv = torch.empty(K, Vc, dtype=torch.float32, device=vw.device)
+        ce = torch.empty(K, Vc, Vc, dtype=torch.float32, device=vw.device)
+        fk = torch.empty(K, D, dtype=torch.float32, device=vw.device)
+    else:
+        cv, ce, fk = out                 # caller-owned buffers (no allocation on this call)
     ws = _workspace("class", lib().sh_class_side_workspace_bytes(K, Vc, D), vw.device)
     thr = -1.0 if prune_threshold is None else float(prune_threshold)
     check(lib().sh_dev_class_side(ctypes.byref(params.struct), ptr(vw), ptr(ew), ptr(ci), K, Vc, thr, int(prune_in_place),
-                                  int(remove_self_loop), ptr(cv), ptr(ce), ptr(out), ptr(ws), ws.numel(), stream()))
-    return cv, ce, out
+                                  int(remove_self_loop), ptr(cv), ptr(ce), ptr(fk), ptr(ws), ws.numel(), stream()))
+    return cv, ce, fk
 
 
 def gnn_forward_class(params, class_vertices, class_edges, class_ingredients, prune_threshold=None):
