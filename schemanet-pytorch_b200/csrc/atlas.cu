@@ -36,7 +36,100 @@ class_vertices_kernel(const float *__restrict__ vw, int K, int Vc, float *__rest
 //   keep(i, j) = cv[k,i] > thr && cv[k,j] > thr          (:157-163, the bmm of the 0/1 vertex mask with itself)
 //   x = keep ? ew : 0 ; in place: ew = 0 where !keep      (:164-166)
 //   ce = nan_to_num(clamp_min(x, 0) / sum_j clamp_min(x, 0))   (:168)
-template <int kChunks>   // kChunks > 0: row cached in registers (Vc <= 128*kChunks, Vc % 4 == 0); 0: generic two-pass
+// Fast path (Vc <= 128*kChunks, Vc % 8 == 0, 16-byte aligned): a warp owns runs of 8 consecutive rows of one class, so the
+// keep-mask of its 32 columns per chunk (identical for every row of the class) is built once and held in ONE register
+// per chunk group; the next row's loads are issued before the current row is reduced; rows whose sum is an ordinary
+// positive number skip the per-element nan_to_num.
+template <int kChunks>
+__global__ void __launch_bounds__(256)
+class_edges_fast_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, int Vc, float thr, int prune,
+                        int prune_in_place, int remove_self_loop, float *__restrict__ ce)
+{
+    constexpr int RUN = 8;
+    const int lane = threadIdx.x & 31;
+    const int units_per_class = Vc / RUN;
+    const int64_t units = (int64_t)K * units_per_class;
+    const int wpb = blockDim.x >> 5;
+    for (int64_t u = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); u < units; u += (int64_t)gridDim.x * wpb) {
+        const int k = (int)(u / units_per_class), i0 = (int)(u % units_per_class) * RUN;
+        const float *cvk = cv + (size_t)k * Vc;
+        // bit (4*c + e) of `mask`: column (c*32 + lane)*4 + e survives the prune
+        unsigned mask = 0xffffffffu;
+        if (prune) {
+            mask = 0;
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                const int j = (c * kWarp + lane) * 4;
+                if (j < Vc) {
+                    const float4 m = *reinterpret_cast<const float4 *>(cvk + j);
+                    mask |= ((m.x > thr ? 1u : 0u) | (m.y > thr ? 2u : 0u) | (m.z > thr ? 4u : 0u) | (m.w > thr ? 8u : 0u)) << (4 * c);
+                }
+            }
+        }
+        float4 cur[kChunks], nxt[kChunks];
+        float *src = ew + ((size_t)k * Vc + i0) * Vc;
+        float *dst = ce + ((size_t)k * Vc + i0) * Vc;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            const int j = (c * kWarp + lane) * 4;
+            nxt[c] = (j < Vc) ? *reinterpret_cast<const float4 *>(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll 1
+        for (int r = 0; r < RUN; ++r) {
+            const int i = i0 + r;
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) cur[c] = nxt[c];
+            if (r + 1 < RUN) {
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) {
+                    const int j = (c * kWarp + lane) * 4;
+                    if (j < Vc) nxt[c] = *reinterpret_cast<const float4 *>(src + (size_t)(r + 1) * Vc + j);
+                }
+            }
+            const bool keep_i = !prune || cvk[i] > thr;
+            const unsigned rowmask = keep_i ? mask : 0u;
+            float acc = 0.0f;
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                const int j = (c * kWarp + lane) * 4;
+                if (j < Vc) {
+                    float4 x = cur[c];
+                    const unsigned mb = (rowmask >> (4 * c)) & 15u;
+                    if (mb != 15u) {
+                        // in-place prune of the parameter (schema_net.py:164); entries that are already zero (every
+                        // call after the first) are not rewritten -- same memory image, half the HBM writes
+                        const float4 z = make_float4((mb & 1u) ? x.x : 0.f, (mb & 2u) ? x.y : 0.f, (mb & 4u) ? x.z : 0.f, (mb & 8u) ? x.w : 0.f);
+                        if (prune_in_place && (z.x != x.x || z.y != x.y || z.z != x.z || z.w != x.w))
+                            *reinterpret_cast<float4 *>(src + (size_t)r * Vc + j) = z;
+                        x = z;
+                    }
+                    x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+                    acc += (x.x + x.y) + (x.z + x.w);
+                    cur[c] = x;
+                }
+            }
+            acc = warp_sum(acc);
+            // one reciprocal per row (<= 1 ulp from x / acc).  acc == 0 means every entry is 0 -> 0/0 = NaN -> 0 in the
+            // reference: emit zeros.  Only non-finite sums need the element-wise nan_to_num.
+            const bool ordinary = acc < INFINITY && acc >= 0.0f;
+            const float inv = (acc == 0.0f) ? 0.0f : 1.0f / acc;
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                const int j = (c * kWarp + lane) * 4;
+                if (j < Vc) {
+                    float4 o = make_float4(cur[c].x * inv, cur[c].y * inv, cur[c].z * inv, cur[c].w * inv);
+                    if (!ordinary) o = make_float4(nan_to_num0(o.x), nan_to_num0(o.y), nan_to_num0(o.z), nan_to_num0(o.w));
+                    if (remove_self_loop && i >= j && i < j + 4) {
+                        if (i == j) o.x = 0.f; else if (i == j + 1) o.y = 0.f; else if (i == j + 2) o.z = 0.f; else o.w = 0.f;
+                    }
+                    __stcs(reinterpret_cast<float4 *>(dst + (size_t)r * Vc + j), o);
+                }
+            }
+        }
+    }
+}
+
+// Generic path: any Vc / alignment, two passes over the row (the second one hits L1/L2).
 __global__ void __launch_bounds__(256)
 class_edges_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, int Vc, float thr, int prune,
                    int prune_in_place, int remove_self_loop, float *__restrict__ ce)
@@ -50,68 +143,23 @@ class_edges_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, 
         float *dst = ce + row * Vc;
         const float *cvk = cv + (size_t)k * Vc;
         const bool keep_i = !prune || cvk[i] > thr;
-        if constexpr (kChunks > 0) {
-            float4 v[kChunks > 0 ? kChunks : 1];
-            float acc = 0.0f;
-#pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-                const int j = (c * kWarp + lane) * 4;
-                v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < Vc) {
-                    float4 x = *reinterpret_cast<const float4 *>(src + j);
-                    if (prune) {
-                        const float4 m = *reinterpret_cast<const float4 *>(cvk + j);
-                        const bool k0 = keep_i && m.x > thr, k1 = keep_i && m.y > thr, k2 = keep_i && m.z > thr,
-                                   k3 = keep_i && m.w > thr;
-                        // in-place prune of the parameter (schema_net.py:164); entries that are already zero (every
-                        // call after the first) are not rewritten -- same memory image, half the HBM writes
-                        const bool dirty = (!k0 && x.x != 0.f) || (!k1 && x.y != 0.f) || (!k2 && x.z != 0.f) || (!k3 && x.w != 0.f);
-                        if (prune_in_place && dirty) {
-                            float4 z = make_float4(k0 ? x.x : 0.f, k1 ? x.y : 0.f, k2 ? x.z : 0.f, k3 ? x.w : 0.f);
-                            *reinterpret_cast<float4 *>(src + j) = z;
-                        }
-                        x.x = k0 ? x.x : 0.f; x.y = k1 ? x.y : 0.f; x.z = k2 ? x.z : 0.f; x.w = k3 ? x.w : 0.f;
-                    }
-                    x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
-                    acc += (x.x + x.y) + (x.z + x.w);
-                    v[c] = x;
-                }
+        float acc = 0.0f;
+        for (int j = lane; j < Vc; j += kWarp) {
+            float x = src[j];
+            if (prune) {
+                const bool keep = keep_i && cvk[j] > thr;
+                if (!keep) { if (prune_in_place && x != 0.f) src[j] = 0.f; x = 0.f; }
             }
-            acc = warp_sum(acc);
-            // one reciprocal per row: pruned entries are exact zeros and 0 / acc would take the IEEE-division slow path
-            // for most of the tensor; x * (1 / acc) differs from x / acc by at most 1 ulp and keeps 0 * inf = NaN -> 0
-            const float inv = 1.0f / acc;
-#pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-                const int j = (c * kWarp + lane) * 4;
-                if (j < Vc) {
-                    float4 o = make_float4(nan_to_num0(v[c].x * inv), nan_to_num0(v[c].y * inv),
-                                           nan_to_num0(v[c].z * inv), nan_to_num0(v[c].w * inv));
-                    if (remove_self_loop && i >= j && i < j + 4) {
-                        if (i == j) o.x = 0.f; else if (i == j + 1) o.y = 0.f; else if (i == j + 2) o.z = 0.f; else o.w = 0.f;
-                    }
-                    __stcs(reinterpret_cast<float4 *>(dst + j), o);
-                }
-            }
-        } else {
-            float acc = 0.0f;
-            for (int j = lane; j < Vc; j += kWarp) {
-                float x = src[j];
-                if (prune) {
-                    const bool keep = keep_i && cvk[j] > thr;
-                    if (!keep) { if (prune_in_place && x != 0.f) src[j] = 0.f; x = 0.f; }
-                }
-                acc += fmaxf(x, 0.f);
-            }
-            acc = warp_sum(acc);
-            const float inv = 1.0f / acc;
-            for (int j = lane; j < Vc; j += kWarp) {
-                float x = src[j];   // pruned entries were just zeroed in place or are re-masked here
-                if (prune && !(keep_i && cvk[j] > thr)) x = 0.f;
-                float o = nan_to_num0(fmaxf(x, 0.f) * inv);
-                if (remove_self_loop && i == j) o = 0.f;
-                dst[j] = o;
-            }
+            acc += fmaxf(x, 0.f);
+        }
+        acc = warp_sum(acc);
+        const float inv = 1.0f / acc;
+        for (int j = lane; j < Vc; j += kWarp) {
+            float x = src[j];   // pruned entries were just zeroed in place or are re-masked here
+            if (prune && !(keep_i && cvk[j] > thr)) x = 0.f;
+            float o = nan_to_num0(fmaxf(x, 0.f) * inv);
+            if (remove_self_loop && i == j) o = 0.f;
+            dst[j] = o;
         }
     }
 }
@@ -131,18 +179,21 @@ extern "C" int sh_dev_class_atlas(const float *vertex_weights, float *edge_weigh
     if (class_edges == nullptr) return 0;
     const int prune = prune_threshold >= 0.0f ? 1 : 0;
     const int64_t rows = (int64_t)K * Vc;
-    const int grid = (int)min(ceil_div64(rows, 8), (int64_t)sm_count() * 32);
-    const bool aligned = (Vc % 4 == 0) && ((reinterpret_cast<uintptr_t>(edge_weights) | reinterpret_cast<uintptr_t>(class_edges) |
+    const bool aligned = (Vc % 8 == 0) && ((reinterpret_cast<uintptr_t>(edge_weights) | reinterpret_cast<uintptr_t>(class_edges) |
                                            reinterpret_cast<uintptr_t>(class_vertices)) % 16 == 0);
-    if (aligned && Vc <= 512)
-        SH_LAUNCH("class_edges_kernel", st, class_edges_kernel<4><<<grid, 256, 0, st>>>(edge_weights, class_vertices, K, Vc, prune_threshold, prune,
+    if (aligned && Vc <= 1024) {
+        const int grid = (int)min(ceil_div64(rows / 8, 8), (int64_t)sm_count() * 16);
+        if (Vc <= 512)
+            SH_LAUNCH("class_edges_kernel", st, class_edges_fast_kernel<4><<<grid, 256, 0, st>>>(edge_weights, class_vertices, K, Vc, prune_threshold, prune,
+                                                        prune_in_place, remove_self_loop, class_edges));
+        else
+            SH_LAUNCH("class_edges_kernel", st, class_edges_fast_kernel<8><<<grid, 256, 0, st>>>(edge_weights, class_vertices, K, Vc, prune_threshold, prune,
+                                                        prune_in_place, remove_self_loop, class_edges));
+    } else {
+        const int grid = (int)min(ceil_div64(rows, 8), (int64_t)sm_count() * 32);
+        SH_LAUNCH("class_edges_kernel", st, class_edges_kernel<<<grid, 256, 0, st>>>(edge_weights, class_vertices, K, Vc, prune_threshold, prune,
                                                     prune_in_place, remove_self_loop, class_edges));
-    else if (aligned && Vc <= 1024)
-        SH_LAUNCH("class_edges_kernel", st, class_edges_kernel<8><<<grid, 256, 0, st>>>(edge_weights, class_vertices, K, Vc, prune_threshold, prune,
-                                                    prune_in_place, remove_self_loop, class_edges));
-    else
-        SH_LAUNCH("class_edges_kernel", st, class_edges_kernel<0><<<grid, 256, 0, st>>>(edge_weights, class_vertices, K, Vc, prune_threshold, prune,
-                                                    prune_in_place, remove_self_loop, class_edges));
+    }
     SH_CHECK_LAUNCH();
     return 0;
 }
