@@ -60,7 +60,10 @@ struct GraphSmem {
     float acls[kMaxL];
     float red0[kMaxL];
     float red1[kMaxL];
-    float row[kGraphWarps][2][kMaxL];
+    float row[kGraphWarps][4][kMaxL];   // per warp: row by position (A, G) or by rank (A, G) + duplicate-position values (A, G)
+    int didx[kMaxL];      // position -> index in the duplicate buffer (-1: first occurrence of its code)
+    int multi[kMaxL];     // ranks of the codes that occur more than once
+    int nmulti;
     int n;
     int next_row;
     float max0, max1;
@@ -72,7 +75,7 @@ __device__ __forceinline__ void rank_codes(GraphSmem &s, const int64_t *codes, i
     const int tid = threadIdx.x;
     if (tid < L) s.code[tid] = codes[tid];
     if (tid < kMaxL) s.cnt[tid] = 0;
-    if (tid == 0) { s.n = 0; s.next_row = 0; }
+    if (tid == 0) { s.n = 0; s.next_row = 0; s.nmulti = 0; }
     __syncthreads();
     int occ = 0, first = 1;
     int64_t c = 0;
@@ -98,8 +101,15 @@ __device__ __forceinline__ void rank_codes(GraphSmem &s, const int64_t *codes, i
         s.start[r] = acc;
     }
     __syncthreads();
-    if (tid < L) s.pos[s.start[rank] + occ] = tid;
-    if (tid < n) s.loc[tid] = tid;
+    if (tid < L) {
+        s.pos[s.start[rank] + occ] = tid;
+        // duplicates are numbered in (rank, occurrence) order: start[r] - r entries precede rank r's chain
+        s.didx[tid] = first ? -1 : s.start[rank] - rank + occ - 1;
+    }
+    if (tid < n) {
+        s.loc[tid] = tid;
+        if (s.cnt[tid] > 1) s.multi[atomicAdd(&s.nmulti, 1)] = tid;
+    }
     __syncthreads();
 }
 
@@ -368,6 +378,150 @@ __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// instance edges, scatter formulation (the hot path; the gather version above serves the dense init-time API)
+// ---------------------------------------------------------------------------------------------------------------
+// Most codes of an image occur once, so the [n, n] block-sum matrix is almost a row/column permutation of the attention
+// map.  A warp owns one output row r1 and keeps its n partial sums in a shared-memory row indexed by RANK:
+//   * a column q that is the first occurrence of its code stores (first row of r1) or adds (later rows) its value
+//     straight from registers into slot rank[q] -- one writer per slot, no conflicts, no gather loop;
+//   * the few columns that repeat a code park their value in a side buffer, and one lane per repeated code folds its
+//     chain into the slot afterwards, in ascending position order.
+// The fp32 order per (r1, r2) is again exactly the reference's: rows ascending, columns ascending, one running sum.
+template <bool kFromHeads, int LC>
+__device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, GraphSmem &s, int b)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = a.L, n = s.n;
+    const bool raw = (a.flags & SH_G_RAW_LOGITS) != 0;
+    const bool use_clamp = raw && a.clamp_e != SH_NO_CLAMP;
+    const bool write_back = !kFromHeads && use_clamp && (a.flags & SH_G_WRITE_BACK_CLAMP);
+    const bool mean = (a.flags & SH_G_SUM) == 0;
+    float *bufA = s.row[warp][0], *bufG = s.row[warp][1], *dupA = s.row[warp][2], *dupG = s.row[warp][3];
+    const float w0 = __ldg(a.w_e), w1 = __ldg(a.w_e + 1);
+    const int nmulti = s.nmulti;
+
+    // image-constant per-lane column info: destination slot of column q = lane + 32 t (>= 0: rank slot, < 0: ~dup index)
+    int slot[LC];
+    float cnt_inv[LC];  // 1 / (positions of the output code r2 = lane + 32 t), for the block mean
+#pragma unroll
+    for (int t = 0; t < LC; ++t) {
+        const int q = lane + kWarp * t;
+        slot[t] = (q < L) ? (s.didx[q] < 0 ? s.rank[q] : ~s.didx[q]) : 0x40000000;   // 0x40000000: no column
+        cnt_inv[t] = (q < n) ? 1.0f / (float)s.cnt[q] : 1.0f;
+    }
+    const int nt = (n + kWarp - 1) / kWarp;
+
+    // Software pipeline over (output row, position) pairs: the attention row and the geometry row of the NEXT pair are
+    // requested before the current pair is reduced, including across output rows (most codes have a single position,
+    // so without this every row would expose a full DRAM round trip).
+    auto grab = [&]() {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(&s.next_row, 1);
+        return __shfl_sync(kFull, r, 0);
+    };
+    auto load_geo = [&](int p, float (&g)[LC]) {
+#pragma unroll
+        for (int t = 0; t < LC; ++t) {
+            const int q = lane + kWarp * t;
+            g[t] = (q < L) ? __ldg(a.geo + (size_t)p * L + q) : 0.0f;
+        }
+    };
+    float x[LC], xn[LC], g[LC], gn[LC];
+    int r1 = grab();
+    if (r1 < n) {
+        load_row<kFromHeads, LC>(a, b, s.pos[s.start[r1]], lane, xn);
+        load_geo(s.pos[s.start[r1]], gn);
+    }
+    while (r1 < n) {
+        const int r1_next = grab();
+        const int k_begin = s.start[r1], k_end = s.start[r1 + 1];
+        for (int k = k_begin; k < k_end; ++k) {
+            const int p = s.pos[k];
+#pragma unroll
+            for (int t = 0; t < LC; ++t) { x[t] = xn[t]; g[t] = gn[t]; }
+            const int p_next = (k + 1 < k_end) ? s.pos[k + 1] : (r1_next < n ? s.pos[s.start[r1_next]] : -1);
+            if (p_next >= 0) {
+                load_row<kFromHeads, LC>(a, b, p_next, lane, xn);
+                load_geo(p_next, gn);
+            }
+            if (raw) {
+                if (write_back) {
+#pragma unroll
+                    for (int t = 0; t < LC; ++t) {
+                        const int q = lane + kWarp * t;
+                        if (q < L && x[t] < a.clamp_e) a.attn[((size_t)b * L + p) * L + q] = -INFINITY;  // :335
+                    }
+                }
+                warp_softmax<LC>(x, L, lane, a.clamp_e, use_clamp);
+            }
+            __syncwarp();
+            if (k == k_begin) {
+#pragma unroll
+                for (int t = 0; t < LC; ++t) {
+                    if (slot[t] >= 0) { if (slot[t] < kMaxL) { bufA[slot[t]] = x[t]; bufG[slot[t]] = g[t]; } }
+                    else { dupA[~slot[t]] = x[t]; dupG[~slot[t]] = g[t]; }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < LC; ++t) {
+                    if (slot[t] >= 0) { if (slot[t] < kMaxL) { bufA[slot[t]] = bufA[slot[t]] + x[t]; bufG[slot[t]] = bufG[slot[t]] + g[t]; } }
+                    else { dupA[~slot[t]] = x[t]; dupG[~slot[t]] = g[t]; }
+                }
+            }
+            __syncwarp();
+            for (int m = lane; m < nmulti; m += kWarp) {     // fold the repeated codes' chains, ascending positions
+                const int r = s.multi[m];
+                const int base = s.start[r] - r, len = s.cnt[r] - 1;
+                float va = bufA[r], vg = bufG[r];
+                for (int kk = 0; kk < len; ++kk) { va = va + dupA[base + kk]; vg = vg + dupG[base + kk]; }
+                bufA[r] = va;
+                bufG[r] = vg;
+            }
+        }
+        __syncwarp();
+
+        // epilogue: block mean, row normalisation, nan_to_num, 2->1 mix
+        // block mean = sum / (cnt1 * cnt2) (utils.cpp:12) as a multiplication by the two precomputed reciprocals: at most
+        // 2 ulp from the reference's division (it is exactly 1.0 for the usual single-occurrence codes) and it keeps 14
+        // IEEE-division sequences per output row out of an issue-bound kernel
+        const float c1_inv = mean ? 1.0f / (float)(k_end - k_begin) : 1.0f;
+        float ea[LC], eg[LC];
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int t = 0; t < LC; ++t) {
+            const int r2 = lane + kWarp * t;
+            ea[t] = 0.0f; eg[t] = 0.0f;
+            if (t < nt && r2 < n) {
+                const float sc = mean ? c1_inv * cnt_inv[t] : 1.0f;
+                ea[t] = bufA[r2] * sc;
+                eg[t] = bufG[r2] * sc;
+                s0 += eg[t];
+                s1 += ea[t];
+            }
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        // one reciprocal per row and channel (<= 1 ulp from x / s); a row whose sums are finite and non-zero has only
+        // finite entries, so nan_to_num (large_scale_feat_to_e.cpp:135) is only applied to the other rows
+        const float inv0 = 1.0f / s0, inv1 = 1.0f / s1;
+        const bool clean = isfinite(inv0) && isfinite(inv1) && isfinite(s0) && isfinite(s1);
+        float *o = a.edges + (size_t)b * L * L + (size_t)r1 * L;
+#pragma unroll
+        for (int t = 0; t < LC; ++t) {
+            const int r2 = lane + kWarp * t;
+            if (r2 < n) {
+                float v0 = eg[t] * inv0, v1 = ea[t] * inv1;
+                if (!clean) { v0 = nan_to_num0(v0); v1 = nan_to_num0(v1); }
+                o[r2] = v0 * w0 + v1 * w1;                     // :140
+            } else if (r2 < L && (a.flags & SH_G_ZERO_PAD)) {
+                o[r2] = 0.0f;                                  // match.py:54 padding, produced in place
+            }
+        }
+        r1 = r1_next;
+    }
+}
+
 template <bool kFromHeads, int LC>
 __global__ void __launch_bounds__(kGraphThreads) instance_graph_kernel(GraphArgs a)
 {
@@ -380,7 +534,7 @@ __global__ void __launch_bounds__(kGraphThreads) instance_graph_kernel(GraphArgs
         }
         if (a.vertex_w) build_vertices<kFromHeads, LC>(a, s, b);
         if (a.edges) {
-            build_edges<kFromHeads, false, LC>(a, s, b);
+            build_edges_scatter<kFromHeads, LC>(a, s, b);
             if (a.flags & SH_G_ZERO_PAD) {   // rows n..L-1 of the [L, L] slot
                 float *o = a.edges + (size_t)b * a.L * a.L;
                 for (int i = s.n * a.L + threadIdx.x; i < a.L * a.L; i += blockDim.x) o[i] = 0.0f;

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-export SCHEMANET_DISC_MODE=${SCHEMANET_DISC_MODE:-}
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"discretize_tc" -s 1 -c 1 -o gpurun_out/prof_disc python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2> gpurun_out/ncu.err; tail -3 gpurun_out/ncu.err
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"instance_graph" -s 1 -c 1 -o gpurun_out/prof_graph python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2> gpurun_out/ncu.err; tail -3 gpurun_out/ncu.err
