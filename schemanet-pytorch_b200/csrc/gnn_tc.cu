@@ -33,13 +33,15 @@ constexpr int G_BK = 32;
 constexpr int G_THREADS = 192;
 constexpr int kABytes = G_BM * G_BK * 4;                 // 16 KB
 
-enum { EPI_STORE_SPLIT = 0, EPI_LN_RELU_T_SPLIT = 1, EPI_LN_RELU_ROWS = 2 };
+enum { EPI_STORE_SPLIT = 0, EPI_LN_RELU_T_SPLIT = 1, EPI_LN_RELU_ROWS = 2, EPI_BIAS_ROWS = 3 };
+constexpr int kMaxDim = 1024;   // largest embed_dim the bias staging buffer holds
 
 struct GemmTcArgs {
     int G;                 // batch of graphs (adj GEMM) or 1 (linear GEMM over flattened rows)
     int rows_per_graph;    // n_fixed
     int M_total;           // rows of the A operand per batch entry
     int K_total;           // reduction length upper bound
+    int N_total;           // output columns (embed_dim): tiles of 256 columns, ld of the row-major outputs
     const int32_t *k_sizes;   // adj GEMM: [G] active size n_g of each graph (rows and reduction range) or null
     const int32_t *row_sizes; // epilogue: [graphs] number of real rows per graph (masks LayerNorm outputs) or null
     int identity_tail;        // adj GEMM: rows >= n_g carry an identity diagonal (class graphs compacted to their
@@ -102,7 +104,7 @@ struct GemmPlan {
     static constexpr int kStages = CTAS == 1 ? 2 : 3;
     static constexpr int kBar = kStages * kStage;
     static constexpr int kParam = kBar + 256;
-    static constexpr int kStageOut = kParam + 3 * G_BN * 4;
+    static constexpr int kStageOut = kParam + (2 * G_BN + kMaxDim) * 4;   // gamma, beta (LN: 256 wide) + bias (up to kMaxDim)
     static constexpr int kTotal = kStageOut + 4 * 32 * 33 * 4 + 1024;
 };
 
@@ -120,14 +122,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
     uint64_t *tmem_full = empty + S;
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 2);
-    float *s_bias = (float *)(smem + P::kParam), *s_gamma = s_bias + G_BN, *s_beta = s_gamma + G_BN;
+    float *s_gamma = (float *)(smem + P::kParam), *s_beta = s_gamma + G_BN, *s_bias = s_beta + G_BN;
     float *s_out = (float *)(smem + P::kStageOut);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;     // 0 = the CTA that issues the MMAs
     const int unit = (int)blockIdx.x / CTAS, num_units = (int)gridDim.x / CTAS;
 
-    if (EPI != EPI_STORE_SPLIT)
+    if (EPI == EPI_LN_RELU_T_SPLIT || EPI == EPI_LN_RELU_ROWS)
         for (int i = threadIdx.x; i < G_BN; i += G_THREADS) { s_bias[i] = a.bias[i]; s_gamma[i] = a.gamma[i]; s_beta[i] = a.beta[i]; }
+    if (EPI == EPI_BIAS_ROWS)
+        for (int i = threadIdx.x; i < a.N_total; i += G_THREADS) s_bias[i] = a.bias[i];
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -143,12 +147,14 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
 
     constexpr int UB = G_BM * CTAS;                      // rows per work unit (a CTA, or a CTA pair)
     const int ub_per = ceil_div(a.M_total, UB);
-    const int tiles = a.G * ub_per;
+    const int nb_per = a.N_total / G_BN;                 // 256-column output tiles (1 unless embed_dim > 256)
+    const int tiles = a.G * ub_per * nb_per;
 
     // every role of every CTA walks the same unit list and applies the same skip rule
 #define TILE_LOOP_BEGIN                                                                                   \
     for (int t = unit; t < tiles; t += num_units) {                                                       \
-        const int g = t / ub_per, ub = t % ub_per;                                                        \
+        const int nb = t % nb_per, gu = t / nb_per;   /* column tile fastest: neighbours share the A rows */ \
+        const int g = gu / ub_per, ub = gu % ub_per;                                                      \
         const int mb = ub * CTAS + rank;   /* this CTA's 128-row block */                                 \
         const int n_g = (a.k_sizes && a.G > 1) ? a.k_sizes[g] : a.K_total;                                \
         if (a.G > 1 && !a.identity_tail && ub * UB >= n_g) continue;                                      \
@@ -178,16 +184,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                         mbar_arrive_expect_tx(&full[stage], P::kStage);
                         tma_load_3d(s, &tmAh, &full[stage], kb * G_BK, mb * G_BM, g);
                         tma_load_3d(s + kABytes, &tmAl, &full[stage], kb * G_BK, mb * G_BM, g);
-                        tma_load_3d(s + 2 * kABytes, &tmBh, &full[stage], kb * G_BK, 0, gb);
-                        tma_load_3d(s + 2 * kABytes + P::kBBytesL, &tmBl, &full[stage], kb * G_BK, 0, gb);
+                        tma_load_3d(s + 2 * kABytes, &tmBh, &full[stage], kb * G_BK, nb * G_BN, gb);
+                        tma_load_3d(s + 2 * kABytes + P::kBBytesL, &tmBl, &full[stage], kb * G_BK, nb * G_BN, gb);
                     } else {
                         // both CTAs' bytes complete on the LEADER's barrier (the only one the MMA issuer waits on)
                         const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
                         if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * P::kStage);
                         tma_load_3d_pair(s, &tmAh, lead_full, kb * G_BK, mb * G_BM, g);
                         tma_load_3d_pair(s + kABytes, &tmAl, lead_full, kb * G_BK, mb * G_BM, g);
-                        tma_load_3d_pair(s + 2 * kABytes, &tmBh, lead_full, kb * G_BK, rank * P::kBRows, gb);
-                        tma_load_3d_pair(s + 2 * kABytes + P::kBBytesL, &tmBl, lead_full, kb * G_BK, rank * P::kBRows, gb);
+                        tma_load_3d_pair(s + 2 * kABytes, &tmBh, lead_full, kb * G_BK, nb * G_BN + rank * P::kBRows, gb);
+                        tma_load_3d_pair(s + 2 * kABytes + P::kBBytesL, &tmBl, lead_full, kb * G_BK, nb * G_BN + rank * P::kBRows, gb);
                     }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
@@ -251,13 +257,25 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                 // warp-level view: this warp owns rows [mb*128 + wq*32, +32) of graph g
                 const int m_warp = mb * G_BM + wq * 32;
                 const int rows_valid = min(32, a.rows_per_graph - m_warp);
-                float *oh = a.out_hi + ((size_t)g * a.rows_per_graph + m_warp) * G_BN;
-                float *ol = a.out_lo + ((size_t)g * a.rows_per_graph + m_warp) * G_BN;
+                float *oh = a.out_hi + ((size_t)g * a.rows_per_graph + m_warp) * a.N_total + nb * G_BN;
+                float *ol = a.out_lo + ((size_t)g * a.rows_per_graph + m_warp) * a.N_total + nb * G_BN;
 #pragma unroll 1
                 for (int c = 0; c < G_BN / 32; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-                    store_chunk_rows<true>(s_out + wq * 32 * 33, v, lane, oh + c * 32, ol + c * 32, G_BN, rows_valid);
+                    store_chunk_rows<true>(s_out + wq * 32 * 33, v, lane, oh + c * 32, ol + c * 32, a.N_total, rows_valid);
+                }
+            } else if (EPI == EPI_BIAS_ROWS) {
+                // Z[m, nb*256 + :] = acc + bias (embed_dim > 256: LayerNorm needs the whole row and runs as its own kernel)
+                const int m_warp = mb * G_BM + wq * 32;
+                float *o = a.out_rows + (size_t)m_warp * a.N_total + nb * G_BN;
+#pragma unroll 1
+                for (int c = 0; c < G_BN / 32; ++c) {
+                    float v[32];
+                    tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += s_bias[nb * G_BN + c * 32 + j];
+                    store_chunk_rows<false>(s_out + wq * 32 * 33, v, lane, o + c * 32, nullptr, a.N_total, min(32, a.M_total - m_warp));
                 }
             } else {
                 // z = acc + bias; LayerNorm over the 256 columns this thread owns; ReLU   (gnn.py:31,45)
@@ -547,11 +565,58 @@ class_adj_prep_kernel(const float *__restrict__ ce, int K, int Vc, int ldk, int 
 // ---------------------------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------------
+// embed_dim > 256: LayerNorm + ReLU as its own pass over Z = Y W^T + b (the GEMM epilogue cannot hold a row wider than
+// one 256-column accumulator).  One CTA per (32-node slab, graph); a warp normalises 4 rows (two-pass mean / variance).
+// kTranspose: stage the slab in shared memory and write H^T hi/lo for the next layer's adjacency GEMM (coalesced along
+// the node index, zeros for nodes >= n_g); otherwise overwrite Z with H in place (the pooling reads rows).
+template <bool kTranspose>
+__global__ void __launch_bounds__(256)
+ln_relu_wide_kernel(float *__restrict__ Z, const int32_t *__restrict__ row_sizes, int n_fixed, int ldk, int D,
+                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float *__restrict__ xt_hi,
+                    float *__restrict__ xt_lo)
+{
+    extern __shared__ float slab[];   // kTranspose: [32][D + 1]
+    const int g = blockIdx.y, i0 = blockIdx.x * 32;
+    const int n_g = row_sizes ? row_sizes[g] : n_fixed;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rr = warp; rr < 32; rr += 8) {
+        const int i = i0 + rr;
+        const bool live = i < n_g;
+        float *z = Z + ((size_t)g * n_fixed + i) * D;
+        float mean = 0.0f, rstd = 0.0f;
+        if (live) {
+            float sum = 0.0f;
+            for (int dd = lane; dd < D; dd += kWarp) sum += z[dd];
+            mean = warp_sum(sum) / (float)D;
+            float var = 0.0f;
+            for (int dd = lane; dd < D; dd += kWarp) { const float t = z[dd] - mean; var = fmaf(t, t, var); }
+            rstd = 1.0f / sqrtf(warp_sum(var) / (float)D + eps);
+        }
+        for (int dd = lane; dd < D; dd += kWarp) {
+            const float y = live ? fmaxf((z[dd] - mean) * rstd * gamma[dd] + beta[dd], 0.0f) : 0.0f;
+            if (kTranspose) slab[rr * (D + 1) + dd] = y;
+            else if (live) z[dd] = y;
+        }
+    }
+    if (kTranspose) {
+        __syncthreads();
+        const int i = i0 + lane;
+        if (i < ldk)
+            for (int dd = warp; dd < D; dd += 8) {
+                float h, l;
+                split_tf32(i < n_fixed ? slab[lane * (D + 1) + dd] : 0.0f, h, l);
+                const size_t o = ((size_t)g * D + dd) * ldk + i;
+                xt_hi[o] = h;
+                xt_lo[o] = l;
+            }
+    }
+}
+
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 bool gnn_tc_supported(int D, int n_fixed)
 {
-    return D == G_BN && n_fixed >= 32 && encode_tiled_fn() != nullptr;
+    return D % G_BN == 0 && D <= kMaxDim && n_fixed >= 32 && encode_tiled_fn() != nullptr;
 }
 
 struct TcBuffers {
@@ -613,7 +678,7 @@ static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const c
         SH_CHECK_CUDA(cudaFuncSetAttribute(gemm3x_kernel<EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kTotal));
         configured = true;
     }
-    const int units = a.G * ceil_div(a.M_total, G_BM * CTAS);
+    const int units = a.G * ceil_div(a.M_total, G_BM * CTAS) * (a.N_total / G_BN);
     const int num_units = min(units, sm_count() / CTAS);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(num_units * CTAS);
@@ -693,7 +758,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
         SH_CHECK_LAUNCH();
         // Y = Adj X
         GemmTcArgs a{};
-        a.G = G; a.rows_per_graph = n_fixed; a.M_total = n_fixed; a.K_total = n_fixed;
+        a.G = G; a.rows_per_graph = n_fixed; a.M_total = n_fixed; a.K_total = n_fixed; a.N_total = D;
         a.k_sizes = k_sizes; a.identity_tail = identity_tail; a.batched_b = 1;
         a.out_hi = b.y_hi; a.out_lo = b.y_lo;
         CUtensorMap m1[4] = {adjm[0], adjm[1], xtm[0], xtm[1]};
@@ -701,13 +766,33 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
         if (launch_gemm3x<EPI_STORE_SPLIT>(m1, m1p, a, "gnn_adj_gemm_tc", st)) return 1;
         // H = relu(LN(Y W^T + b))
         GemmTcArgs c{};
-        c.G = 1; c.rows_per_graph = n_fixed; c.M_total = G * n_fixed; c.K_total = D; c.row_sizes = row_sizes; c.batched_b = 0;
+        c.G = 1; c.rows_per_graph = n_fixed; c.M_total = G * n_fixed; c.K_total = D; c.N_total = D; c.row_sizes = row_sizes; c.batched_b = 0;
         c.bias = p->lin_b[l]; c.gamma = p->ln_w[l]; c.beta = p->ln_b[l]; c.eps = p->ln_eps;
         c.out_hi = b.xt_hi; c.out_lo = b.xt_lo; c.ldk = ldk; c.out_rows = b.h_rows;
         CUtensorMap m2[4] = {ym[0], ym[1], wm[0], wm[1]};
         CUtensorMap m2p[4] = {ym[0], ym[1], wm2[0], wm2[1]};
-        if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
-        else { if (launch_gemm3x<EPI_LN_RELU_T_SPLIT>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
+        if (D == G_BN) {
+            if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
+            else { if (launch_gemm3x<EPI_LN_RELU_T_SPLIT>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
+        } else {
+            // wide embeddings: bias in the GEMM epilogue, LayerNorm + ReLU (+ transpose/split) as a separate pass
+            if (launch_gemm3x<EPI_BIAS_ROWS>(m2, m2p, c, "gnn_linear_tc", st)) return 1;
+            dim3 grid(ceil_div(ldk, 32), G);
+            if (last) {
+                SH_LAUNCH("gnn_ln_relu_wide", st, ln_relu_wide_kernel<false><<<grid, 256, 0, st>>>(b.h_rows, row_sizes, n_fixed, ldk, D, p->ln_w[l],
+                                                                                                  p->ln_b[l], p->ln_eps, nullptr, nullptr));
+            } else {
+                const size_t smem = (size_t)32 * (D + 1) * sizeof(float);
+                static bool configured = false;
+                if (!configured) {
+                    SH_CHECK_CUDA(cudaFuncSetAttribute(ln_relu_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (kMaxDim + 1) * 4));
+                    configured = true;
+                }
+                SH_LAUNCH("gnn_ln_relu_wide", st, ln_relu_wide_kernel<true><<<grid, 256, smem, st>>>(b.h_rows, row_sizes, n_fixed, ldk, D, p->ln_w[l],
+                                                                                                    p->ln_b[l], p->ln_eps, b.xt_hi, b.xt_lo));
+            }
+            SH_CHECK_LAUNCH();
+        }
     }
     dim3 grid(chunks, G);
     SH_LAUNCH("gnn_pool_rows", st, pool_rows_kernel<<<grid, 256, 0, st>>>(b.h_rows, vertex_w, ld_v, row_sizes, n_fixed, D, chunks, partial));

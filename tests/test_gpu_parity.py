@@ -322,13 +322,14 @@ def test_class_side_large_tile_path():
     rel_close(got, ho.gnn_forward(params, nodes, edges, ids, None), what="gnn class side")
 
 
-@pytest.mark.parametrize("K,Vc,masked", [(3, 300, False), (5, 1024, False), (9, 196, True), (2, 33, True)])
-def test_gnn_tensor_core_path_vs_oracle(K, Vc, masked):
+@pytest.mark.parametrize("K,Vc,masked,D", [(3, 300, False, 256), (5, 1024, False, 256), (9, 196, True, 256), (2, 33, True, 256),
+                                          (3, 300, True, 512), (2, 500, False, 1024)])
+def test_gnn_tensor_core_path_vs_oracle(K, Vc, masked, D):
     """embed_dim 256 takes the tcgen05 3xTF32 path (adjacency prep, TMA-fed UMMA, LayerNorm fused in the TMEM
     epilogue); it must meet the same 1e-5 bar against the fp32 oracle as the CUDA-core path."""
     from schema_inference.graph import Matcher
     gen = torch.Generator().manual_seed(80 + Vc)
-    M, D = 1500, 256
+    M = 1500
     params = ho.synth_gnn(M, D, seed=81)
     params["layers.0.norm.weight"] = torch.rand(D, generator=gen) + 0.5
     params["layers.1.norm.bias"] = torch.randn(D, generator=gen) * 0.1
