@@ -6,73 +6,71 @@ nearest-codeword search runs in libschemahead (`sh_dev_discretize`): the [n*bs, 
 There is no CPU fallback: CPU tensors raise.
 """
 import logging
-from typing import Tuple
+from typing import Sequence, Tuple
 
 import torch
-import torch.nn as nn
-import torch.nn.functional as F
+from torch import nn
 
 from schemanet_b200 import native
 
+_LOG = logging.getLogger("discretization")
+
 
 class Discretization(nn.Module):
-    def __init__(
-        self,
-        size: int,
-        dim: int,
-        detach_input_seq: bool = True,
-        uniform_range: Tuple[float, float] = [-1, 1]
-    ):
+    """Visual vocabulary (codebook) of `size` words of dimension `dim`; maps every token to its nearest word.
+
+    detach_input_seq: the tokens are detached before matching (always true for the frozen backbone of the head).
+    uniform_range: initialisation interval of the codebook before `initial_vocabulary` loads the k-means result.
+    """
+
+    def __init__(self, size: int, dim: int, detach_input_seq: bool = True,
+                 uniform_range: Sequence[float] = (-1, 1)):
         super().__init__()
-        self.logger = logging.getLogger("discretization")
-        self.size = size
-        self.dim = dim
+        self.logger = _LOG
+        self.size, self.dim = size, dim
         self.detach_input_seq = detach_input_seq
-        self.logger.info("Creating discretization with size: %d, dimension: %d", size, dim)
         self.vocabulary = nn.Embedding(size, dim)
-        self._reset_parameters(uniform_range)
-        self.kernel_mode = native.DISC_AUTO
-        self.activate()
+        lo, hi = uniform_range
+        nn.init.uniform_(self.vocabulary.weight, lo, hi)
+        _LOG.info("codebook of %d words x %d dims, U[%.2f, %.2f] init", size, dim, lo, hi)
+        self.kernel_mode = native.DISC_AUTO      # SH_DISC_* selector of the CUDA path
+        self._activate = True                    # True: the returned sequence is replaced by the matched codewords
 
-    def _reset_parameters(self, uniform_range: Tuple[float, float]):
-        self.logger.info("Initializing with Uniform[%.2f, %.2f]", uniform_range[0], uniform_range[1])
-        nn.init.uniform_(self.vocabulary.weight, uniform_range[0], uniform_range[1])
-
-    def initial_vocabulary(self, vocabulary_fp: str):
-        self.logger.info("Loading from external vocabulary...")
-        vocabulary: torch.Tensor = torch.load(vocabulary_fp, map_location="cpu")
-        if vocabulary.shape[0] > self.size:
-            self.logger.warning("Too much external vocabulary, using random picked vocabulary...")
-            vocabulary = vocabulary[torch.randperm(vocabulary.shape[0])][:self.size]
-        with torch.no_grad():
-            self.vocabulary.weight.copy_(vocabulary)
-
-    def deactivate(self):
-        self.logger.debug("Deactivated discretization!")
-        self._activate = False
-
+    # -- state ----------------------------------------------------------------------------------------------------
     def activate(self):
-        self.logger.debug("Activated discretization!")
         self._activate = True
 
+    def deactivate(self):
+        self._activate = False
+
+    def initial_vocabulary(self, vocabulary_fp: str):
+        """Loads a [n_words, dim] tensor saved by the k-means extraction; a random subset if it has too many rows."""
+        words: torch.Tensor = torch.load(vocabulary_fp, map_location="cpu")
+        surplus = words.shape[0] - self.size
+        if surplus > 0:
+            _LOG.warning("external vocabulary has %d words too many: keeping a random subset", surplus)
+            words = words[torch.randperm(words.shape[0])[:self.size]]
+        with torch.no_grad():
+            self.vocabulary.weight.copy_(words)
+
+    # -- matching -------------------------------------------------------------------------------------------------
     def encode(self, seq: torch.Tensor) -> Tuple[torch.Tensor, torch.LongTensor]:
-        if self.detach_input_seq:
-            seq = seq.detach()
-        n, bs = seq.shape[:2]
-        flat = seq.reshape(n * bs, self.dim)
-        weight = self.vocabulary.weight
-        train_vocab = torch.is_grad_enabled() and weight.requires_grad
-        gathered = None
-        if self._activate and not train_vocab:
-            gathered = torch.empty(n * bs, self.dim, dtype=torch.float32, device=flat.device)
-        ingredients = native.discretize(flat.detach(), weight.detach(), out_seq=gathered, mode=self.kernel_mode)
+        tokens = seq.detach() if self.detach_input_seq else seq
+        n, bs = tokens.shape[0], tokens.shape[1]
+        flat = tokens.reshape(n * bs, self.dim)
+        codebook = self.vocabulary.weight
+        # a trainable codebook keeps the gather as an autograd op (reference :66-67); otherwise it is fused in CUDA
+        trainable = torch.is_grad_enabled() and codebook.requires_grad
+        fused_out = None
+        if self._activate and not trainable:
+            fused_out = torch.empty(n * bs, self.dim, dtype=torch.float32, device=flat.device)
+        ingredients = native.discretize(flat.detach(), codebook.detach(), out_seq=fused_out, mode=self.kernel_mode)
         if self._activate:
-            # with a trainable vocabulary the gather stays an autograd op, as in the reference (:66-67)
-            flat = self.vocabulary(ingredients) if train_vocab else gathered
+            flat = self.vocabulary(ingredients) if trainable else fused_out
         return flat.reshape(n, bs, self.dim), ingredients.reshape(n, bs)
 
     def forward(self, seq: torch.Tensor) -> Tuple[torch.Tensor, torch.LongTensor]:
-        """seq [n, bs, dim] -> (encoded sequence [n, bs, dim], matched ingredient of every token [n, bs])."""
-        t = seq.shape[2]
-        assert int(t) == self.dim, f"dimension {seq.shape[2]} not match to {self.dim}"
+        """seq [n, bs, dim] -> (sequence [n, bs, dim] (codewords if activated), ingredient id of every token [n, bs])."""
+        got = int(seq.shape[2])
+        assert got == self.dim, f"dimension {got} not match to {self.dim}"
         return self.encode(seq)

@@ -1,26 +1,27 @@
 """Drop-in for `discretization.visual_word_encoder` (discretization/visual_word_encoder.py:10-68) and for the
 `DiscretizationJitWrapper` of scripts/save_backbone_jit.py:121-131 (the module the reference traces into
 `discretization-jit.pth`)."""
-from typing import Dict
+from typing import Dict, Optional
 
 import torch
-import torch.nn as nn
+from torch import nn
 from torch.utils.hooks import RemovableHandle
 
 from .discretization import Discretization
 
 
 class Adapter:
-    """Strips the cls token before discretization and puts it back afterwards (ViT: one cls token)."""
+    """ViT sequences carry one cls token in front: `adapt` strips it, `reconstruct` puts it back."""
 
     def __init__(self):
         self.shape: torch.Size = None
+        self.cls_token: Optional[torch.Tensor] = None
 
     def adapt(self, x: torch.Tensor) -> torch.Tensor:
-        self.cls_token = x[:1]
-        return x[1:]
+        self.cls_token, patches = x[:1], x[1:]
+        return patches
 
-    def reconstruct(self, x: torch.Tensor, match: torch.Tensor) -> torch.Tensor:
+    def reconstruct(self, x: torch.Tensor, match: torch.Tensor):
         return torch.cat((self.cls_token, x), dim=0), match
 
 
@@ -33,33 +34,36 @@ class DiscretizationJitWrapper(nn.Module):
         self.adapter = Adapter()
 
     def forward(self, dummy_input: torch.Tensor):
-        seq = self.adapter.adapt(dummy_input)
-        output, match = self.discretization(seq)
-        return self.adapter.reconstruct(output, match)
+        patches = self.adapter.adapt(dummy_input)
+        encoded, match = self.discretization(patches)
+        return self.adapter.reconstruct(encoded, match)
 
 
 class VisualWordEncoder:
+    """Forward hook that discretises the output of `encode_layer` inside a backbone and records what it did in
+    `mid_dict` ("origin_seq", "encoded_seq", "match")."""
+
+    KEYS = ("origin_seq", "encoded_seq", "match")
+
     def __init__(self, model: nn.Module, encode_layer: str, discretization: Discretization):
         self.encode_layer = encode_layer
         self.discretization = discretization
         self.adapter = Adapter()
+        self.mid_dict: Dict[str, torch.Tensor] = dict.fromkeys(self.KEYS)
         self.hook = self.register_forward_hooks(model)
-        self.mid_dict: Dict[str, torch.Tensor] = {"origin_seq": None, "encoded_seq": None, "match": None}
+
+    def _on_forward(self, module, inputs, output):
+        encoded, match = self.discretization(self.adapter.adapt(output))
+        encoded, match = self.adapter.reconstruct(encoded, match)
+        self.mid_dict.update(origin_seq=output, encoded_seq=encoded, match=match)
+        return encoded
 
     def register_forward_hooks(self, model: nn.Module) -> RemovableHandle:
-        raw_model = model.module if isinstance(model, nn.parallel.DistributedDataParallel) else model
-        for name, module in raw_model.named_modules():
-            if name == self.encode_layer:
-                def forward_hook(module, input, output):
-                    self.mid_dict["origin_seq"] = output
-                    seq, match = self.discretization(self.adapter.adapt(output))
-                    seq, match = self.adapter.reconstruct(seq, match)
-                    self.mid_dict["encoded_seq"] = seq
-                    self.mid_dict["match"] = match
-                    return seq
-                return module.register_forward_hook(forward_hook)
+        if isinstance(model, nn.parallel.DistributedDataParallel):
+            model = model.module
+        target = dict(model.named_modules()).get(self.encode_layer)
+        return None if target is None else target.register_forward_hook(self._on_forward)
 
     def clear(self):
         self.hook.remove()
-        for k in self.mid_dict:
-            self.mid_dict[k] = None
+        self.mid_dict = dict.fromkeys(self.KEYS)

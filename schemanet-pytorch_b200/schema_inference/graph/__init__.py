@@ -1,20 +1,24 @@
 """Drop-in for `schema_inference.graph` (schema_inference/graph/__init__.py:14-57)."""
-import collections
-from typing import Dict, List
+from collections import OrderedDict
 
 import torch
-import torch.nn as nn
-
-from .schema_net import SchemaNet, InstanceGraphs
-from .match import Matcher
-from .gnn import GNN
+from torch import nn
 
 from schema_inference.utils import IngredientModelWrapper
+from .gnn import GNN
+from .match import Matcher
+from .schema_net import Atlas, InstanceGraphs, SchemaNet
+
+__all__ = ["SchemaNet", "Matcher", "GNN", "SchemaNetPredictor", "InstanceGraphs", "Atlas"]
 
 
 class SchemaNetPredictor(nn.Module):
-    """ingredient model -> SchemaNet instance graphs -> matcher.  Returns an OrderedDict with "pred" [bs, K], the
-    atlas tensors and, with requires_graph=True, the (padded) instance graphs, "ingredients" and "attn_cls"."""
+    """backbone + discretisation (no grad) -> instance IR-graphs -> match against the class IR-atlas.
+
+    forward(x) returns an OrderedDict: "pred" [bs, K] first, then the atlas ("class_vertices", "class_edges",
+    "class_ingredients"); with requires_graph=True also the instance graphs (padded by the matcher, as in the
+    reference), "ingredients" and "attn_cls".
+    """
 
     def __init__(self, ingredient_wrapper: IngredientModelWrapper, schema_net: SchemaNet, matcher: Matcher):
         super().__init__()
@@ -24,16 +28,14 @@ class SchemaNetPredictor(nn.Module):
         self.num_classes = schema_net.num_classes
 
     def forward(self, x: torch.Tensor, requires_graph: bool = False):
-        ret = collections.OrderedDict()
         with torch.no_grad():
-            output = self.ingredient_wrapper(x)
-        instance_dict: Dict[str, List[torch.Tensor]] = self.schema_net(
-            ingredients=output["ingredients"], attn=output["attn"], attn_cls=output["attn_cls"])
-        class_dict = self.schema_net.get_atlas()
-        ret["pred"] = self.matcher(instance_dict=instance_dict, class_dict=class_dict)
-        ret.update(class_dict)
+            taps = self.ingredient_wrapper(x)
+        graphs = self.schema_net(ingredients=taps["ingredients"], attn=taps["attn"], attn_cls=taps["attn_cls"])
+        atlas = self.schema_net.get_atlas()
+        out = OrderedDict(pred=self.matcher(instance_dict=graphs, class_dict=atlas))
+        out.update(atlas)
         if requires_graph:
-            ret.update(instance_dict)
-            ret["ingredients"] = output["ingredients"]
-            ret["attn_cls"] = output["attn_cls"]
-        return ret
+            out.update(graphs)
+            for key in ("ingredients", "attn_cls"):
+                out[key] = taps[key]
+        return out
