@@ -261,6 +261,51 @@ pool_fc_kernel(const float *__restrict__ partial, int chunks, int D, int n_fixed
     }
 }
 
+// out[r, o] = sum_k A[r, k] W[o, k] for a tall-skinny A (the (M+1)-row embedding table).  (The generic tiled GEMM
+// launches only ~18 CTAs for this shape and took 0.11 ms.)
+// kRows rows per CTA; a lane keeps its slice of the kRows x D input rows in registers (D <= 256: 8 columns per lane), so
+// the inner loop is 8 coalesced loads of a W row + kRows*8 FMAs + kRows shuffle reductions per output feature.
+template <int kRows>
+__global__ void __launch_bounds__(256)
+rows_linear_kernel(const float *__restrict__ A, const float *__restrict__ W, int rows, int D, float *__restrict__ out)
+{
+    const int r0 = blockIdx.x * kRows, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float a[kRows][8];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = u * kWarp + lane;
+            a[i][u] = (r0 + i < rows && k < D) ? __ldg(A + (size_t)(r0 + i) * D + k) : 0.0f;
+        }
+    for (int o = warp; o < D; o += 8) {
+        const float *w = W + (size_t)o * D;
+        float wk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = u * kWarp + lane;
+            wk[u] = k < D ? __ldg(w + k) : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fmaf(a[i][u], wk[u], acc);
+            acc = warp_sum(acc);
+            if (lane == 0 && r0 + i < rows) out[(size_t)(r0 + i) * D + o] = acc;
+        }
+    }
+}
+
+int launch_rows_linear(const float *A, const float *W, int rows, int D, float *out, cudaStream_t st)
+{
+    SH_REQUIRE(D <= 256, "rows_linear: D <= 256 expected");
+    SH_LAUNCH("gnn_embed_table_linear", st,
+              rows_linear_kernel<4><<<ceil_div(rows, 4), 256, 0, st>>>(A, W, rows, D, out));
+    SH_CHECK_LAUNCH();
+    return 0;
+}
+
 }  // namespace sh
 
 using namespace sh;

@@ -157,10 +157,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
         const int g = gu / ub_per, ub = gu % ub_per;                                                      \
         const int mb = ub * CTAS + rank;   /* this CTA's 128-row block */                                 \
         const int n_g = (a.k_sizes && a.G > 1) ? a.k_sizes[g] : a.K_total;                                \
-        if (a.G > 1 && !a.identity_tail && ub * UB >= n_g) continue;                                      \
+        /* units past the graph are skipped, except when the epilogue must still write their (zero) rows */ \
+        if (EPI == EPI_STORE_SPLIT && a.G > 1 && !a.identity_tail && ub * UB >= n_g) continue;            \
         /* k-blocks [0, kA) cover the active range; with identity_tail a unit that holds rows >= n_g       \
            additionally visits the k-blocks of its own diagonal that are not in [0, kA) */                 \
-        const int kA = (a.G > 1 && a.identity_tail && ub * UB >= n_g) ? 0 : ceil_div(n_g, G_BK);           \
+        const int kA = (a.G > 1 && a.identity_tail && ub * UB >= n_g) ? 0 : max(1, ceil_div(n_g, G_BK));   \
         int k2s = 0, k2c = 0;                                                                             \
         if (a.identity_tail && (ub + 1) * UB > n_g) {                                                     \
             k2s = max(kA, ub * (UB / G_BK));                                                              \
@@ -279,8 +280,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                 }
             } else {
                 // z = acc + bias; LayerNorm over the 256 columns this thread owns; ReLU   (gnn.py:31,45)
-                const int gg = m / a.rows_per_graph, i = m % a.rows_per_graph;   // flattened rows -> (graph, node)
-                const bool in_range = m < a.M_total;
+                // linear GEMM: flattened rows -> (graph, node); adjacency GEMM with a fused LayerNorm: (g, row in graph)
+                const int gg = a.G > 1 ? g : m / a.rows_per_graph, i = a.G > 1 ? m : m % a.rows_per_graph;
+                const bool in_range = a.G > 1 ? m < a.rows_per_graph : m < a.M_total;
                 const int n_node = (in_range && a.row_sizes) ? a.row_sizes[gg] : a.rows_per_graph;
                 const bool valid = in_range && i < n_node;
                 float sum = 0.0f;
@@ -314,8 +316,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                     if (EPI == EPI_LN_RELU_ROWS) {
                         // rows of masked nodes are never read downstream (pooling stops at n_g): store all rows in range
                         const int m_warp = mb * G_BM + wq * 32;
-                        store_chunk_rows<false>(s_out + wq * 32 * 33, v, lane, a.out_rows + (size_t)m_warp * G_BN + c * 32,
-                                                nullptr, G_BN, min(32, a.M_total - m_warp));
+                        const size_t row0 = (a.G > 1 ? (size_t)g * a.rows_per_graph : 0) + m_warp;
+                        store_chunk_rows<false>(s_out + wq * 32 * 33, v, lane, a.out_rows + row0 * G_BN + c * 32, nullptr, G_BN,
+                                                min(32, (a.G > 1 ? a.rows_per_graph : a.M_total) - m_warp));
                     } else {
                         // H^T[gg, n, i] as hi/lo: lanes hold consecutive nodes i -> coalesced 128-byte stores; nodes
                         // beyond n_g are written as zeros (they are the zero-padded K range of the next adj GEMM)
@@ -620,7 +623,7 @@ bool gnn_tc_supported(int D, int n_fixed)
 }
 
 struct TcBuffers {
-    float *adj_hi, *adj_lo, *xt_hi, *xt_lo, *y_hi, *y_lo, *w_hi, *w_lo, *h_rows;
+    float *adj_hi, *adj_lo, *xt_hi, *xt_lo, *xt2_hi, *xt2_lo, *y_hi, *y_lo, *w_hi, *w_lo, *h_rows;
     int32_t *n_act, *old_of_new;
     int64_t *pid;
     float *pvw;
@@ -640,6 +643,8 @@ static TcBuffers carve_tc(void *base, int G, int n_fixed, int D)
     b.adj_lo = (float *)(p + off); off += adj_b;
     b.xt_hi = (float *)(p + off); off += xt_b;
     b.xt_lo = (float *)(p + off); off += xt_b;
+    b.xt2_hi = (float *)(p + off); off += xt_b;
+    b.xt2_lo = (float *)(p + off); off += xt_b;
     b.y_hi = (float *)(p + off); off += y_b;
     b.y_lo = (float *)(p + off); off += y_b;
     b.w_hi = (float *)(p + off); off += w_b;
@@ -732,43 +737,68 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
                          const TcBuffers &b, int chunks, float *partial, cudaStream_t st)
 {
     const int D = p->embed_dim, ldk = b.ldk;
+    // Layer-0 shortcut (embed_dim 256): (Adj X0) W0^T = Adj (X0 W0^T) and X0 = Emb[ids], so the first Linear is applied to
+    // the (M+1)-row embedding TABLE once (a tiny fp32 GEMM) instead of to every node of every graph; layer 0 then is a
+    // single adjacency GEMM with bias + LayerNorm + ReLU fused in its epilogue.  The table product is staged in the
+    // (still unused) Y_lo buffer, which it fits whenever the batch has at least M+1 node slots.
+    const bool fuse0 = D == G_BN && (int64_t)(p->num_codes + 1) <= (int64_t)G * n_fixed;
+    const float *table = p->embedding;
+    if (fuse0) {
+        if (launch_rows_linear(p->embedding, p->lin_w[0], p->num_codes + 1, D, b.y_lo, st)) return 1;
+        table = b.y_lo;
+    }
     {
         dim3 grid2(ceil_div(ldk, 32), D / 32, G);
-        SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(p->embedding, ids, ld_ids, row_sizes, n_fixed, ldk, D, b.xt_hi, b.xt_lo));
+        SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(table, ids, ld_ids, row_sizes, n_fixed, ldk, D, b.xt_hi, b.xt_lo));
         SH_CHECK_LAUNCH();
     }
     CUtensorMap adjm[2], xtm[2], ym[2], wm[2];
     if (tmap3(&adjm[0], b.adj_hi, n_fixed, n_fixed, G, ldk, (uint64_t)n_fixed * ldk, G_BM)) return 1;
     if (tmap3(&adjm[1], b.adj_lo, n_fixed, n_fixed, G, ldk, (uint64_t)n_fixed * ldk, G_BM)) return 1;
-    if (tmap3(&xtm[0], b.xt_hi, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
-    if (tmap3(&xtm[1], b.xt_lo, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
     if (tmap3(&ym[0], b.y_hi, D, (uint64_t)G * n_fixed, 1, D, 0, G_BM)) return 1;
     if (tmap3(&ym[1], b.y_lo, D, (uint64_t)G * n_fixed, 1, D, 0, G_BM)) return 1;
     if (tmap3(&wm[0], b.w_hi, D, D, 1, D, 0, G_BN)) return 1;
     if (tmap3(&wm[1], b.w_lo, D, D, 1, D, 0, G_BN)) return 1;
-    CUtensorMap xtm2[2], wm2[2];      // CTA pairs stage half of the B tile each
-    if (tmap3(&xtm2[0], b.xt_hi, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN / 2)) return 1;
-    if (tmap3(&xtm2[1], b.xt_lo, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN / 2)) return 1;
+    CUtensorMap wm2[2];               // CTA pairs stage half of the B tile each
     if (tmap3(&wm2[0], b.w_hi, D, D, 1, D, 0, G_BN / 2)) return 1;
     if (tmap3(&wm2[1], b.w_lo, D, D, 1, D, 0, G_BN / 2)) return 1;
+    // node features ping-pong between two X^T buffers (a fused-LayerNorm adjacency GEMM must not overwrite its own B)
+    float *xin_hi = b.xt_hi, *xin_lo = b.xt_lo, *xout_hi = b.xt2_hi, *xout_lo = b.xt2_lo;
 
     for (int l = 0; l < p->num_layers; ++l) {
         const bool last = (l == p->num_layers - 1);
-        SH_LAUNCH("gnn_split_weights", st, split_kernel<<<64, 256, 0, st>>>(p->lin_w[l], (int64_t)D * D, b.w_hi, b.w_lo));
-        SH_CHECK_LAUNCH();
-        // Y = Adj X
+        CUtensorMap xtm[2], xtm2[2];
+        if (tmap3(&xtm[0], xin_hi, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
+        if (tmap3(&xtm[1], xin_lo, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
+        if (tmap3(&xtm2[0], xin_hi, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN / 2)) return 1;
+        if (tmap3(&xtm2[1], xin_lo, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN / 2)) return 1;
+        CUtensorMap m1[4] = {adjm[0], adjm[1], xtm[0], xtm[1]};
+        CUtensorMap m1p[4] = {adjm[0], adjm[1], xtm2[0], xtm2[1]};
         GemmTcArgs a{};
         a.G = G; a.rows_per_graph = n_fixed; a.M_total = n_fixed; a.K_total = n_fixed; a.N_total = D;
         a.k_sizes = k_sizes; a.identity_tail = identity_tail; a.batched_b = 1;
+        if (l == 0 && fuse0) {
+            // H1 = relu(LN(Adj (X0 W0^T) + b0)) in one kernel
+            a.row_sizes = row_sizes;
+            a.bias = p->lin_b[0]; a.gamma = p->ln_w[0]; a.beta = p->ln_b[0]; a.eps = p->ln_eps;
+            a.out_hi = xout_hi; a.out_lo = xout_lo; a.ldk = ldk; a.out_rows = b.h_rows;
+            if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
+            else { if (launch_gemm3x<EPI_LN_RELU_T_SPLIT>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
+            float *t;
+            t = xin_hi; xin_hi = xout_hi; xout_hi = t;
+            t = xin_lo; xin_lo = xout_lo; xout_lo = t;
+            continue;
+        }
+        SH_LAUNCH("gnn_split_weights", st, split_kernel<<<64, 256, 0, st>>>(p->lin_w[l], (int64_t)D * D, b.w_hi, b.w_lo));
+        SH_CHECK_LAUNCH();
+        // Y = Adj X
         a.out_hi = b.y_hi; a.out_lo = b.y_lo;
-        CUtensorMap m1[4] = {adjm[0], adjm[1], xtm[0], xtm[1]};
-        CUtensorMap m1p[4] = {adjm[0], adjm[1], xtm2[0], xtm2[1]};
         if (launch_gemm3x<EPI_STORE_SPLIT>(m1, m1p, a, "gnn_adj_gemm_tc", st)) return 1;
         // H = relu(LN(Y W^T + b))
         GemmTcArgs c{};
         c.G = 1; c.rows_per_graph = n_fixed; c.M_total = G * n_fixed; c.K_total = D; c.N_total = D; c.row_sizes = row_sizes; c.batched_b = 0;
         c.bias = p->lin_b[l]; c.gamma = p->ln_w[l]; c.beta = p->ln_b[l]; c.eps = p->ln_eps;
-        c.out_hi = b.xt_hi; c.out_lo = b.xt_lo; c.ldk = ldk; c.out_rows = b.h_rows;
+        c.out_hi = xin_hi; c.out_lo = xin_lo; c.ldk = ldk; c.out_rows = b.h_rows;
         CUtensorMap m2[4] = {ym[0], ym[1], wm[0], wm[1]};
         CUtensorMap m2p[4] = {ym[0], ym[1], wm2[0], wm2[1]};
         if (D == G_BN) {
@@ -789,7 +819,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
                     configured = true;
                 }
                 SH_LAUNCH("gnn_ln_relu_wide", st, ln_relu_wide_kernel<true><<<grid, 256, smem, st>>>(b.h_rows, row_sizes, n_fixed, ldk, D, p->ln_w[l],
-                                                                                                    p->ln_b[l], p->ln_eps, b.xt_hi, b.xt_lo));
+                                                                                                    p->ln_b[l], p->ln_eps, xin_hi, xin_lo));
             }
             SH_CHECK_LAUNCH();
         }

@@ -16,4 +16,7 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
                          const int64_t *class_ingredients, float prune_threshold, int chunks, float *partial,
                          void *workspace, cudaStream_t st);
 
+// out[rows, D] = A[rows, D] W^T with W [D, D] (fp32 CUDA-core GEMM from gnn.cu; used for the embedding-table shortcut)
+int launch_rows_linear(const float *A, const float *W, int rows, int D, float *out, cudaStream_t st);
+
 }  // namespace sh
