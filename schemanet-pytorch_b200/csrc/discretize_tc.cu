@@ -28,9 +28,11 @@ using namespace tc;
 constexpr int TC_BM = 128;       // token rows per tile (UMMA M)
 constexpr int TC_BK = 32;        // fp32 per k-block = one 128-byte swizzle row
 constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;    // two warps per TMEM lane quarter: each takes half of a tile's column chunks
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int kOverflowMark = -1;
-constexpr int kCandStride = kCandSlots + 1;   // slot kCandSlots absorbs the stores of a full list
+constexpr int kListSlots = 14;                // per-half shared-memory list capacity (4 stages + 2 lists fit in 227 KB)
+constexpr int kCandStride = kListSlots + 1;   // slot kListSlots absorbs the stores of a full list
 
 struct DiscTcArgs {
     int64_t R;
@@ -54,7 +56,9 @@ struct DiscTcSmem {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = TC_STAGES * kStageBytes;
     static constexpr int kCandOffset = kBarOffset + 256;
-    static constexpr int kTotal = kCandOffset + TC_BM * kCandStride * 8 + 1024;   // + slack for 1024-B alignment
+    // two candidate lists per row (one per column half) + the halves' running minima / counts
+    static constexpr int kHalfOffset = kCandOffset + 2 * TC_BM * kCandStride * 8;
+    static constexpr int kTotal = kHalfOffset + 2 * TC_BM * 8 + 1024;   // + slack for 1024-B alignment
 };
 
 // kBf16: operands are bf16 copies (64 elements per 128-byte swizzle row, kind::f16, UMMA K = 16) instead of the fp32
@@ -74,7 +78,9 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 2);
     float *cand_s = (float *)(smem + S::kCandOffset);
-    int *cand_i = (int *)(cand_s + TC_BM * kCandStride);
+    int *cand_i = (int *)(cand_s + 2 * TC_BM * kCandStride);
+    float *half_m = (float *)(smem + S::kHalfOffset);
+    int *half_c = (int *)(half_m + 2 * TC_BM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -82,7 +88,7 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], TC_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);
@@ -139,9 +145,11 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
         // ===================== epilogue: fused score + running argmin + near-tie candidates =====================
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;              // which half of every tile's column chunks this warp scans
         const int row_in_tile = wq * 32 + lane;
-        float *my_s = cand_s + row_in_tile * kCandStride;
-        int *my_i = cand_i + row_in_tile * kCandStride;
+        float *my_s = cand_s + (half * TC_BM + row_in_tile) * kCandStride;
+        int *my_i = cand_i + (half * TC_BM + row_in_tile) * kCandStride;
+        constexpr int kChunksPerHalf = (BN / 32) / 2;
         const float cmax = sqrtf(__uint_as_float(*a.cmax_bits));
         int as = 0;
         uint32_t aphase = 0;
@@ -150,13 +158,13 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const bool valid = row < a.R;
             const float band = valid ? a.beta * (kBf16 ? 3.90625e-3f : 9.765625e-4f) * sqrtf(a.xn[row]) * cmax : 0.0f;
             float m_run = INFINITY;
-            int cnt = 0;                  // candidates stored; kCandSlots means "full: some may have been lost"
+            int cnt = 0;                  // candidates stored; kListSlots means "full: some may have been lost"
             for (int nb = 0; nb < a.num_n_blocks; ++nb) {
                 mbar_wait(&tmem_full[as], aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = half * kChunksPerHalf; c < (half + 1) * kChunksPerHalf; ++c) {
                     const int n_base = nb * BN + c * 32;
                     if (n_base >= a.M || (a.debug & 1)) break;
                     float v[32];
@@ -183,7 +191,7 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         for (int j = 0; j < 32; ++j) {
                             my_s[cnt] = v[j];                       // unconditional store, conditional advance
                             my_i[cnt] = n_base + j;
-                            cnt = min(cnt + ((v[j] <= thr) ? 1 : 0), kCandSlots);   // == kCandSlots: list is full
+                            cnt = min(cnt + ((v[j] <= thr) ? 1 : 0), kListSlots);   // == kListSlots: list is full
                         }
                     }
                 }
@@ -192,20 +200,38 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
-            if (valid) {
-                const float thr = m_run + band;
-                const bool overflow = cnt >= kCandSlots;   // a full list may have dropped a candidate: exact rescan
+            // merge the two column halves of each row: half 1 publishes its minimum / count, half 0 finalises
+            half_m[half * TC_BM + row_in_tile] = m_run;
+            half_c[half * TC_BM + row_in_tile] = cnt;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            if (half == 0 && valid) {
+                const float m_all = fminf(m_run, half_m[TC_BM + row_in_tile]);
+                const float thr = m_all + band;
+                bool overflow = false;
                 int keep = 0, first = 0;
-                if (!overflow)
-                    for (int t = 0; t < cnt; ++t)
-                        if (my_s[t] <= thr) { if (keep == 0) first = my_i[t]; a.cand_idx[row * kCandSlots + keep] = my_i[t]; ++keep; }
-                if (overflow) a.cand_count[row] = kOverflowMark;
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int cnt_h = half_c[h * TC_BM + row_in_tile];
+                    const float *ls = cand_s + (h * TC_BM + row_in_tile) * kCandStride;
+                    const int *li = cand_i + (h * TC_BM + row_in_tile) * kCandStride;
+                    // a full list may have dropped candidates -- harmless if even its minimum is out of reach
+                    if (cnt_h >= kListSlots && half_m[h * TC_BM + row_in_tile] <= thr) overflow = true;
+                    for (int t = 0; t < min(cnt_h, kListSlots) && !overflow; ++t)
+                        if (ls[t] <= thr) {
+                            if (keep == 0) first = li[t];
+                            if (keep < kCandSlots) a.cand_idx[row * kCandSlots + keep] = li[t];
+                            else overflow = true;
+                            ++keep;
+                        }
+                }
+                if (overflow) a.cand_count[row] = kOverflowMark;   // exact rescan of the whole row
                 else {
                     a.cand_count[row] = keep;
                     if (keep == 1)
                         a.out_idx[(row % a.idx_rows) * a.idx_row_stride + (row / a.idx_rows) * a.idx_col_stride] = first;
                 }
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");   // lists are reused by the next row block
         }
     }
     tc_fence_before();
