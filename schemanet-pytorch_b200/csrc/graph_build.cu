@@ -8,15 +8,17 @@
 // and the clamp + softmax the Python callers run first (schema_inference/graph/schema_net.py:295-297,334-336),
 // optionally also the head-mean/slicing prologue (schema_inference/utils/ingredient_model_wrapper.py:57-69).
 //
-// Design (HBM-bound stage: 153,664 B of attention per image are read exactly once, nothing else is large):
-//   * one CTA per image, 8 warps, several CTAs resident per SM so that >= 32 attention rows are in flight per SM;
-//   * codes are ranked in shared memory (sorted-unique order == the reference's std::map iteration order);
-//   * a warp owns one OUTPUT row r1 (= one distinct code) at a time and walks that code's positions p in ascending
-//     order; each attention row is read with fully coalesced 128 B warp loads, soft-maxed in registers
-//     (warp-shuffle max/sum), staged in shared memory, then every lane gathers the columns of the codes r2 it owns
-//     and adds them, in ascending column order, into register accumulators.  The fp32 summation order is therefore
-//     EXACTLY the reference's (p ascending, q ascending, one scalar accumulator from 0.0f; utils.cpp:9) and there
-//     are no atomics on the accumulators or the output;
+// Design.  153,664 B of attention per image are read exactly once and nothing else is large, but the stage is bound by
+// instruction issue and dependent-instruction latency, not by HBM: ~20 thread-instructions per attention element
+// (clamp, exp, two normalisations, scatter, mix) against the ~23 an SM can issue per element at HBM speed.
+//   * one CTA per image (small batches: per (image, split)), 12 warps, two CTAs per SM;
+//   * codes are ranked by a bitonic sort of (code, position) keys, 30 of 36 steps in registers by warp shuffle
+//     (sorted-unique order == the reference's std::map iteration order);
+//   * a warp owns a range of OUTPUT rows r1 (= distinct codes) and walks their positions p in ascending order; each
+//     attention row is read with fully coalesced 128 B warp loads (the next row is requested before the current one
+//     is reduced), soft-maxed in registers (warp-shuffle max/sum) and scattered to shared-memory slots indexed by the
+//     rank of the column's code.  The fp32 summation order is EXACTLY the reference's (p ascending, q ascending, one
+//     scalar accumulator from 0.0f; utils.cpp:9) and there are no atomics on the accumulators or the output;
 //   * block means, row normalisation (warp-shuffle row sum), nan_to_num and the 2->1 attribute mix are fused into
 //     the epilogue; the output row is written once, coalesced.
 #include "common.cuh"
@@ -26,7 +28,8 @@ namespace sh {
 constexpr int kMaxL = 256;           // tokens per image supported by the shared-memory layout (reference: 196)
 constexpr int kGraphThreads = 256;   // 8 warps
 constexpr int kGraphWarps = kGraphThreads / kWarp;
-constexpr int kMaxLaneCols = kMaxL / kWarp;   // columns / output codes owned by one lane (template LC <= this)
+constexpr int kMaxLaneCols = kMaxL / kWarp;
+static_assert(kGraphThreads == kMaxL, "rank_codes sorts one (code, position) pair per thread");   // columns / output codes owned by one lane (template LC <= this)
 
 struct GraphArgs {
     const int64_t *ingredients;   // [B, L]
@@ -49,10 +52,11 @@ struct GraphArgs {
     float *dense_out;                  // [B, n_max, n_max, 2]
 };
 
-struct GraphSmem {
+template <int kWarps>
+struct GraphSmemT {
     int64_t code[kMaxL];
     int rank[kMaxL];      // rank of the code at position p among the image's sorted distinct codes
-    int first[kMaxL];     // 1 if p is the first position holding its code
+    float cinvm[kMaxL];   // by rank: 1 / cnt (1 when block sums are requested), 0 for ranks >= n -- the epilogue's scale + mask
     int cnt[kMaxL];       // positions per distinct code
     int start[kMaxL + 1]; // CSR offsets into pos[]
     int pos[kMaxL];       // positions grouped by code rank, ascending inside a group
@@ -60,114 +64,184 @@ struct GraphSmem {
     float acls[kMaxL];
     float red0[kMaxL];
     float red1[kMaxL];
-    float row[kGraphWarps][4][kMaxL];   // per warp: row by position (A, G) or by rank (A, G) + duplicate-position values (A, G)
+    float row[kWarps][2][kMaxL];   // per warp and channel (A, G): the row by position (gather kernels) or by slot (scatter)
     int didx[kMaxL];      // position -> index in the duplicate buffer (-1: first occurrence of its code)
     int multi[kMaxL];     // ranks of the codes that occur more than once
+    int krow[kMaxL];      // CSR entry -> position | rank << 8 | first << 16 | last << 17 (instance kernel)
     int nmulti;
     int n;
     int next_row;
     float max0, max1;
 };
+using GraphSmem = GraphSmemT<kGraphWarps>;   // the 256-thread kernels
 
-// Ranks the codes of image b.  After this call (and the trailing barrier) rank/cnt/start/pos/n are valid.
-__device__ __forceinline__ void rank_codes(GraphSmem &s, const int64_t *codes, int L)
+
+// Ranks the codes of image b.  After this call (and the trailing barrier) rank/first/cnt/start/pos/didx/multi/n are valid.
+// A bitonic sort of the (code, position) pairs (one pair per thread, 30 of the 36 compare-exchange steps by warp shuffle)
+// replaces the O(L^2) rank loops: sorted order == the reference's std::map iteration order, equal codes stay in ascending
+// position order, so the sorted array IS the CSR position list.  Requires blockDim.x >= kMaxL.
+template <class S>
+__device__ __forceinline__ void rank_codes(S &s, const int64_t *codes, int L)
 {
-    const int tid = threadIdx.x;
-    if (tid < L) s.code[tid] = codes[tid];
-    if (tid < kMaxL) s.cnt[tid] = 0;
-    if (tid == 0) { s.n = 0; s.next_row = 0; s.nmulti = 0; }
-    __syncthreads();
-    int occ = 0, first = 1;
-    int64_t c = 0;
-    if (tid < L) {
-        c = s.code[tid];
-        for (int q = 0; q < tid; ++q)
-            if (s.code[q] == c) { first = 0; ++occ; }
-        s.first[tid] = first;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // scratch aliased onto the per-warp row buffers (not in use while ranking)
+    // (blocks of up to 512 threads: threads >= kMaxL sort padding among themselves and are ignored afterwards)
+    int64_t *xc = reinterpret_cast<int64_t *>((reinterpret_cast<uintptr_t>(&s.row[0][0][0]) + 7) & ~(uintptr_t)7);  // [512] codes
+    int *xp = reinterpret_cast<int *>(&s.row[3][0][0]);                            // [512] positions / 32-bit keys
+    int *wtot = reinterpret_cast<int *>(&s.row[4][0][0]);                          // [16] heads per warp
+    int *wlast = wtot + 16;                                                        // [16] last head index per warp
+    int64_t c = (tid < L) ? codes[tid] : INT64_MAX;   // padding sorts behind every real pair (ties broken by position)
+    int p = tid;
+    if (tid < L) s.code[tid] = c;
+    if (tid == 0) { s.next_row = 0; s.nmulti = 0; }
+    constexpr int64_t kSmall = (1 << 23) - 1;
+    if (!__syncthreads_or(tid < L && (c < 0 || c >= kSmall))) {
+        // usual case (codebook indices): one 32-bit key code << 8 | position per thread, compare-exchange = shuffle + min/max
+        int key = (tid < L) ? ((int)c << 8) | tid : (int)(kSmall << 8) | tid;
+        int *xk = xp;
+#pragma unroll
+        for (int k = 2; k <= kMaxL; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {     // fully unrolled: the 36 (k, j) pairs are compile-time masks
+                int ok;
+                if (j >= kWarp) {
+                    __syncthreads();
+                    xk[tid] = key;
+                    __syncthreads();
+                    ok = xk[tid ^ j];
+                } else {
+                    ok = __shfl_xor_sync(kFull, key, j);
+                }
+                const bool want_min = ((tid & k) == 0) == ((tid & j) == 0);
+                key = want_min ? min(key, ok) : max(key, ok);
+            }
+        }
+        c = key >> 8;
+        p = key & 255;
+    } else {
+#pragma unroll 1
+        for (int k = 2; k <= kMaxL; k <<= 1) {
+#pragma unroll 1
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                int64_t oc;
+                int op;
+                if (j >= kWarp) {
+                    __syncthreads();
+                    xc[tid] = c; xp[tid] = p;
+                    __syncthreads();
+                    oc = xc[tid ^ j]; op = xp[tid ^ j];
+                } else {
+                    oc = __shfl_xor_sync(kFull, c, j);
+                    op = __shfl_xor_sync(kFull, p, j);
+                }
+                const bool other_less = oc < c || (oc == c && op < p);
+                const bool want_min = ((tid & k) == 0) == ((tid & j) == 0);
+                if (want_min == other_less) { c = oc; p = op; }
+            }
+        }
     }
     __syncthreads();
-    int rank = 0;
-    if (tid < L) {
-        for (int q = 0; q < L; ++q) rank += (s.first[q] && s.code[q] < c) ? 1 : 0;
-        s.rank[tid] = rank;
-        atomicAdd(&s.cnt[rank], 1);
-        if (first) atomicAdd(&s.n, 1);
-    }
+    xc[tid] = c;
     __syncthreads();
-    const int n = s.n;
-    for (int r = tid; r <= n; r += blockDim.x) {
-        int acc = 0;
-        for (int k = 0; k < r; ++k) acc += s.cnt[k];
-        s.start[r] = acc;
-    }
+    // run heads (first pair of each distinct code), their ranks by a ballot scan
+    const bool live = tid < L;
+    const bool head = live && (tid == 0 || xc[tid - 1] != c);
+    const unsigned hm = __ballot_sync(kFull, head);
+    if (lane == 0) { wtot[warp] = __popc(hm); wlast[warp] = hm ? warp * kWarp + 31 - __clz(hm) : -1; }
     __syncthreads();
-    if (tid < L) {
-        s.pos[s.start[rank] + occ] = tid;
-        // duplicates are numbered in (rank, occurrence) order: start[r] - r entries precede rank r's chain
-        s.didx[tid] = first ? -1 : s.start[rank] - rank + occ - 1;
+    int before = 0, n = 0, run0 = -1;
+#pragma unroll
+    for (int w = 0; w < kGraphWarps; ++w) {
+        const int tw = wtot[w];
+        if (w < warp) { before += tw; if (wlast[w] >= 0) run0 = wlast[w]; }
+        n += tw;
     }
+    const unsigned le = hm & (0xffffffffu >> (31 - lane));
+    const int rank = before + __popc(le) - 1;
+    if (le) run0 = warp * kWarp + 31 - __clz(le);
+    if (tid == 0) s.n = n;
+    if (live) {
+        const int occ = tid - run0;
+        s.rank[p] = rank;
+        s.pos[tid] = p;
+        s.didx[p] = occ == 0 ? -1 : tid - rank - 1;   // duplicates are numbered in (rank, occurrence) order
+        if (head) { s.start[rank] = tid; s.loc[rank] = rank; }
+    }
+    if (tid == 0) s.start[n] = L;
+    __syncthreads();
     if (tid < n) {
-        s.loc[tid] = tid;
-        if (s.cnt[tid] > 1) s.multi[atomicAdd(&s.nmulti, 1)] = tid;
+        const int len = s.start[tid + 1] - s.start[tid];
+        s.cnt[tid] = len;
+        if (len > 1) s.multi[atomicAdd(&s.nmulti, 1)] = tid;
     }
     __syncthreads();
 }
 
-// One row of (optionally head-averaged) attention logits: lane holds columns q = lane + 32 t.
+// One row of (optionally head-averaged) attention logits: lane holds columns q = lane + 32 t; `fill` for q >= L.
 template <bool kFromHeads, int LC>
-__device__ __forceinline__ void load_row(const GraphArgs &a, int b, int p, int lane, float (&x)[LC])
+__device__ __forceinline__ void load_row(const GraphArgs &a, int b, int p, int lane, float fill, float (&x)[LC])
 {
     const int L = a.L;
     if (kFromHeads) {
         const int T = L + 1;
-        const float *base = a.attn + ((size_t)b * a.H * T + (size_t)(p + 1)) * T + 1;
+        const float *base = a.attn + ((size_t)b * a.H * T + (size_t)(p + 1)) * T + 1 + lane;
 #pragma unroll
         for (int t = 0; t < LC; ++t) {
-            const int q = lane + kWarp * t;
-            float acc = 0.0f;
-            if (q < L) {
-                for (int h = 0; h < a.H; ++h) acc += __ldg(base + (size_t)h * T * T + q);
+            float acc = fill;
+            if (lane + kWarp * t < L) {
+                acc = 0.0f;
+                for (int h = 0; h < a.H; ++h) acc += __ldg(base + (size_t)h * T * T + kWarp * t);
                 acc = acc / (float)a.H;   // torch.mean on CPU: sum over heads, then divide
             }
             x[t] = acc;
         }
     } else {
-        const float *base = a.attn + ((size_t)b * L + p) * L;
+        const float *base = a.attn + ((size_t)b * L + p) * L + lane;
 #pragma unroll
-        for (int t = 0; t < LC; ++t) {
-            const int q = lane + kWarp * t;
-            x[t] = (q < L) ? __ldg(base + q) : 0.0f;
-        }
+        for (int t = 0; t < LC; ++t) x[t] = (lane + kWarp * t < L) ? __ldg(base + kWarp * t) : fill;
     }
 }
 
-// masked_fill(x < clamp, -inf) + softmax over the L valid columns held by the warp (schema_net.py:334-336).
-template <int LC>
-__device__ __forceinline__ void warp_softmax(float (&x)[LC], int L, int lane, float clamp, bool use_clamp)
+__device__ __forceinline__ float rcp_approx(float x)   // MUFU.RCP: <= 1 ulp for normal x
 {
-    float m = -INFINITY;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float ex2_approx(float x)   // MUFU.EX2: ~2 ulp
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// masked_fill(x < clamp, -inf) + softmax over the L valid columns held by the warp (schema_net.py:334-336).
+// Columns q >= L must hold -inf on entry.  exp(x - m) is evaluated as 2^((x - m) log2 e + 64): the 2^64 bias keeps every
+// term a normal number down to x - m = -131 (below the reference's own denormal floor), so nothing is flushed to zero
+// that the reference keeps; it cancels in the normalisation, whose final multiply rounds into the denormal range like
+// the reference's division does.  An all-masked row gives (-inf) - (-inf) = NaN everywhere, exactly like torch.softmax.
+template <int LC>
+__device__ __forceinline__ void warp_softmax(float (&x)[LC], float clamp, bool use_clamp)
+{
+    if (use_clamp) {
 #pragma unroll
-    for (int t = 0; t < LC; ++t) {
-        const int q = lane + kWarp * t;
-        if (q < L) {
-            if (use_clamp && x[t] < clamp) x[t] = -INFINITY;
-            m = fmaxf(m, x[t]);
-        }
+        for (int t = 0; t < LC; ++t) x[t] = x[t] < clamp ? -INFINITY : x[t];
     }
+    float m = x[0];
+#pragma unroll
+    for (int t = 1; t < LC; ++t) m = fmaxf(m, x[t]);
     m = warp_max(m);
     float sum = 0.0f;
 #pragma unroll
     for (int t = 0; t < LC; ++t) {
-        const int q = lane + kWarp * t;
-        // all-masked row: x - m = (-inf) - (-inf) = NaN, exactly like torch.softmax
-        x[t] = (q < L) ? __expf(x[t] - m) : 0.0f;   // ex2.approx path: ~2 ulp, NaN/-inf semantics as expf
+        x[t] = ex2_approx(fmaf(x[t] - m, 1.4426950408889634f, 64.0f));
         sum += x[t];
     }
     sum = warp_sum(sum);
-    // one reciprocal per row instead of 8 IEEE divisions per lane: the masked entries (exact zeros) would send every
-    // division down the slow path (ncu: 55% of this kernel's instructions); the result differs from x / sum by at
-    // most 1 ulp, far inside the 1e-5 tolerance, and 0 * (1/0) = NaN keeps the all-masked-row semantics
-    const float inv = 1.0f / sum;
+    // one reciprocal per row instead of an IEEE division per element (ncu: the masked entries, exact zeros, sent every
+    // division down the slow path -- 55% of this kernel's instructions); <= 2 ulp from x / sum, inside the 1e-5 bar
+    const float inv = rcp_approx(sum);      // sum in [2^64, 2^72): normal
 #pragma unroll
     for (int t = 0; t < LC; ++t) x[t] = x[t] * inv;
 }
@@ -175,25 +249,31 @@ __device__ __forceinline__ void warp_softmax(float (&x)[LC], int L, int lane, fl
 // ---------------------------------------------------------------------------------------------------------------
 // vertices of one image (large_scale_feat_to_v.cpp:78-125)
 // ---------------------------------------------------------------------------------------------------------------
+// The cls-attention row of image b (warp 0 only).  Issued before the codes are ranked so that its DRAM latency is hidden.
 template <bool kFromHeads, int LC>
-__device__ __forceinline__ void build_vertices(const GraphArgs &a, GraphSmem &s, int b)
+__device__ __forceinline__ void load_cls_row(const GraphArgs &a, int b, float (&x)[LC])
+{
+    const int lane = threadIdx.x & 31, L = a.L;
+    const bool raw = (a.flags & SH_G_RAW_LOGITS) != 0;
+    if (kFromHeads) {
+        load_row<true, LC>(a, b, -1, lane, -INFINITY, x);   // row "-1" of the sliced map == the cls row (token 0)
+    } else {
+#pragma unroll
+        for (int t = 0; t < LC; ++t) {
+            const int q = lane + kWarp * t;
+            x[t] = (q < L) ? a.attn_cls[(size_t)b * L + q] : (raw ? -INFINITY : 0.0f);
+        }
+    }
+}
+
+template <bool kFromHeads, int LC, class S>
+__device__ __forceinline__ void build_vertices(const GraphArgs &a, S &s, int b, float (&x)[LC])
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = a.L, n = s.n;
     const bool raw = (a.flags & SH_G_RAW_LOGITS) != 0;
     const bool use_clamp = raw && a.clamp_v != SH_NO_CLAMP;
     if (warp == 0) {
-        float x[LC];
-        if (kFromHeads) {
-            GraphArgs a2 = a;   // row "-1" of the sliced map == the cls row (token 0) of the full map
-            load_row<true, LC>(a2, b, -1, lane, x);
-        } else {
-#pragma unroll
-            for (int t = 0; t < LC; ++t) {
-                const int q = lane + kWarp * t;
-                x[t] = (q < L) ? a.attn_cls[(size_t)b * L + q] : 0.0f;
-            }
-        }
         if (raw) {
             if (!kFromHeads && use_clamp && (a.flags & SH_G_WRITE_BACK_CLAMP)) {
 #pragma unroll
@@ -202,7 +282,7 @@ __device__ __forceinline__ void build_vertices(const GraphArgs &a, GraphSmem &s,
                     if (q < L && x[t] < a.clamp_v) a.attn_cls[(size_t)b * L + q] = -INFINITY;   // schema_net.py:296
                 }
             }
-            warp_softmax(x, L, lane, a.clamp_v, use_clamp);
+            warp_softmax<LC>(x, a.clamp_v, use_clamp);
 #pragma unroll
             for (int t = 0; t < LC; ++t) x[t] = nan_to_num0(x[t]);                        // :297
         }
@@ -255,6 +335,7 @@ __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, in
     const bool use_clamp = raw && a.clamp_e != SH_NO_CLAMP;
     const bool write_back = !kFromHeads && use_clamp && (a.flags & SH_G_WRITE_BACK_CLAMP);
     const bool mean = (a.flags & SH_G_SUM) == 0;
+    const float fill = raw ? -INFINITY : 0.0f;   // columns q >= L: neutral for the soft-max / for the sums
     float *rowA = s.row[warp][0];
     float *rowG = s.row[warp][1];
     float w0 = 0.f, w1 = 0.f;
@@ -287,12 +368,12 @@ __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, in
 
         const int k_begin = s.start[r1], k_end = s.start[r1 + 1];
         float x[LC], xn[LC];
-        load_row<kFromHeads, LC>(a, b, s.pos[k_begin], lane, xn);
+        load_row<kFromHeads, LC>(a, b, s.pos[k_begin], lane, fill, xn);
         for (int k = k_begin; k < k_end; ++k) {
             const int p = s.pos[k];
 #pragma unroll
             for (int t = 0; t < LC; ++t) x[t] = xn[t];
-            if (k + 1 < k_end) load_row<kFromHeads, LC>(a, b, s.pos[k + 1], lane, xn);   // prefetch the next row
+            if (k + 1 < k_end) load_row<kFromHeads, LC>(a, b, s.pos[k + 1], lane, fill, xn);   // prefetch the next row
             float g[LC];
 #pragma unroll
             for (int t = 0; t < LC; ++t) {
@@ -307,7 +388,7 @@ __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, in
                         if (q < L && x[t] < a.clamp_e) a.attn[((size_t)b * L + p) * L + q] = -INFINITY;  // :335
                     }
                 }
-                warp_softmax<LC>(x, L, lane, a.clamp_e, use_clamp);
+                warp_softmax<LC>(x, a.clamp_e, use_clamp);
             }
             __syncwarp();
 #pragma unroll
@@ -382,14 +463,29 @@ __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, in
 // instance edges, scatter formulation (the hot path; the gather version above serves the dense init-time API)
 // ---------------------------------------------------------------------------------------------------------------
 // Most codes of an image occur once, so the [n, n] block-sum matrix is almost a row/column permutation of the attention
-// map.  A warp owns one output row r1 and keeps its n partial sums in a shared-memory row indexed by RANK:
-//   * a column q that is the first occurrence of its code stores (first row of r1) or adds (later rows) its value
-//     straight from registers into slot rank[q] -- one writer per slot, no conflicts, no gather loop;
-//   * the few columns that repeat a code park their value in a side buffer, and one lane per repeated code folds its
-//     chain into the slot afterwards, in ascending position order.
-// The fp32 order per (r1, r2) is again exactly the reference's: rows ascending, columns ascending, one running sum.
-template <bool kFromHeads, int LC>
-__device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, GraphSmem &s, int b)
+// map.  A warp owns a contiguous range of OUTPUT rows r1 (= of CSR entries: the positions of those codes, ascending) and
+// keeps the n partial sums of the current row in a shared-memory buffer indexed by RANK:
+//   * the attention row is read with coalesced 128 B warp loads, soft-maxed in registers, and every column is stored
+//     straight to its destination: rank[q] when q is the first occurrence of its code, n + (duplicate index) otherwise.
+//     The destinations are image constants held in registers as byte offsets, so the scatter is 2 x LC plain STS, no
+//     branches; one writer per slot, no atomics;
+//   * one lane per repeated code then folds its chain of duplicates into the rank slot, in ascending position order.
+// The fp32 order per (r1, r2) is exactly the reference's: rows ascending, columns ascending, one running sum
+// (utils.cpp:9).  The epilogue reads all 32 LC slots; those >= n are masked by a zero in the per-lane reciprocal counts.
+
+#ifdef SH_GRAPH_CLOCKS
+__device__ unsigned long long g_clk[8];
+#define CLK(i) do { if ((threadIdx.x & 31) == 0) { long long now_ = clock64(); atomicAdd(&g_clk[i], (unsigned long long)(now_ - t_)); t_ = now_; } } while (0)
+#else
+#define CLK(i)
+#endif
+#ifdef SH_GRAPH_CLOCKS
+#define RCLK(i) do { long long now_ = clock64(); racc_[i - 5] += now_ - tr_; tr_ = now_; } while (0)
+#else
+#define RCLK(i)
+#endif
+template <bool kFromHeads, int LC, class S>
+__device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, S &s, int b, int split, int nsplit)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = a.L, n = s.n;
@@ -397,150 +493,193 @@ __device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, GraphSme
     const bool use_clamp = raw && a.clamp_e != SH_NO_CLAMP;
     const bool write_back = !kFromHeads && use_clamp && (a.flags & SH_G_WRITE_BACK_CLAMP);
     const bool mean = (a.flags & SH_G_SUM) == 0;
-    float *bufA = s.row[warp][0], *bufG = s.row[warp][1], *dupA = s.row[warp][2], *dupG = s.row[warp][3];
+    const float fill = raw ? -INFINITY : 0.0f;   // columns q >= L: neutral for the soft-max / for the sums
+    float *bufA = &s.row[warp][0][0], *bufG = &s.row[warp][1][0];
     const float w0 = __ldg(a.w_e), w1 = __ldg(a.w_e + 1);
     const int nmulti = s.nmulti;
+    const int n_store = (a.flags & SH_G_ZERO_PAD) ? L : n;          // columns written per output row
 
-    // image-constant per-lane column info: destination slot of column q = lane + 32 t (>= 0: rank slot, < 0: ~dup index)
-    int slot[LC];
-    float cnt_inv[LC];  // 1 / (positions of the output code r2 = lane + 32 t), for the block mean
+    // image constants per lane: destination slot of column q = lane + 32 t
+    int dst[LC];
+    unsigned dupmask = 0;   // bit t: column t of this lane repeats an earlier code (its value is parked, not summed)
 #pragma unroll
     for (int t = 0; t < LC; ++t) {
         const int q = lane + kWarp * t;
-        slot[t] = (q < L) ? (s.didx[q] < 0 ? s.rank[q] : ~s.didx[q]) : 0x40000000;   // 0x40000000: no column
-        cnt_inv[t] = (q < n) ? 1.0f / (float)s.cnt[q] : 1.0f;
-    }
-    const int nt = (n + kWarp - 1) / kWarp;
-
-    // Software pipeline over (output row, position) pairs: the attention row and the geometry row of the NEXT pair are
-    // requested before the current pair is reduced, including across output rows (most codes have a single position,
-    // so without this every row would expose a full DRAM round trip).
-    auto grab = [&]() {
-        int r = 0;
-        if (lane == 0) r = atomicAdd(&s.next_row, 1);
-        return __shfl_sync(kFull, r, 0);
-    };
-    auto load_geo = [&](int p, float (&g)[LC]) {
-#pragma unroll
-        for (int t = 0; t < LC; ++t) {
-            const int q = lane + kWarp * t;
-            g[t] = (q < L) ? __ldg(a.geo + (size_t)p * L + q) : 0.0f;
+        int d = kMaxL - 1;      // sink for the columns q >= L (no real slot: n + duplicates = L <= 255 when it is used)
+        if (q < L) {
+            const int di = s.didx[q];
+            d = di < 0 ? s.rank[q] : n + di;
+            if (di >= 0) dupmask |= 1u << t;
         }
-    };
-    float x[LC], xn[LC], g[LC], gn[LC];
-    int r1 = grab();
-    if (r1 < n) {
-        load_row<kFromHeads, LC>(a, b, s.pos[s.start[r1]], lane, xn);
-        load_geo(s.pos[s.start[r1]], gn);
+        dst[t] = d;
     }
-    while (r1 < n) {
-        const int r1_next = grab();
-        const int k_begin = s.start[r1], k_end = s.start[r1 + 1];
-        for (int k = k_begin; k < k_end; ++k) {
-            const int p = s.pos[k];
+    // one lane per repeated code (lane m -> multi[m]; more than 32 repeated codes fall to the loop below)
+    const bool has_m = lane < nmulti;
+    const int m_r = has_m ? s.multi[lane] : 0;
+    const int m_len = has_m ? s.cnt[m_r] - 1 : 0;
+    const int m_base = n + s.start[m_r] - m_r;
+    for (int j = L + lane; j < kMaxL; j += kWarp) { bufA[j] = 0.0f; bufG[j] = 0.0f; }   // never written, read by the epilogue
+
+    // rows of this CTA (split of the image), then of this warp; CSR entries [k, k_hi)
+    const int r_lo = n * split / nsplit, r_hi = n * (split + 1) / nsplit;
+    const int rows = r_hi - r_lo;
+    const int nwarps = blockDim.x >> 5;
+    int k = s.start[r_lo + rows * warp / nwarps];
+    const int k_hi = s.start[r_lo + rows * (warp + 1) / nwarps];
+    __syncwarp();
+
+    auto load_geo = [&](int p, float (&g)[LC]) {
+        const float *base = a.geo + (size_t)p * L + lane;
 #pragma unroll
-            for (int t = 0; t < LC; ++t) { x[t] = xn[t]; g[t] = gn[t]; }
-            const int p_next = (k + 1 < k_end) ? s.pos[k + 1] : (r1_next < n ? s.pos[s.start[r1_next]] : -1);
-            if (p_next >= 0) {
-                load_row<kFromHeads, LC>(a, b, p_next, lane, xn);
-                load_geo(p_next, gn);
+        for (int t = 0; t < LC; ++t) g[t] = (lane + kWarp * t < L) ? __ldg(base + kWarp * t) : 0.0f;
+    };
+    // Software pipeline over the CSR entries: the attention and geometry rows of the NEXT entry are requested before the
+    // current one is reduced (most codes have a single position: without this every row would expose a DRAM round trip).
+    float x[LC], xn[LC], g[LC], gn[LC];
+    int info_n = 0;
+    if (k < k_hi) {
+        info_n = s.krow[k];
+        load_row<kFromHeads, LC>(a, b, info_n & 255, lane, fill, xn);
+        load_geo(info_n & 255, gn);
+    }
+#ifdef SH_GRAPH_CLOCKS
+    long long tr_ = clock64();
+    long long racc_[3] = {0, 0, 0};
+#endif
+    while (k < k_hi) {
+        const int info = info_n;
+        const int p = info & 255, r1 = (info >> 8) & 255;
+#pragma unroll
+        for (int t = 0; t < LC; ++t) { x[t] = xn[t]; g[t] = gn[t]; }
+        ++k;
+        if (k < k_hi) {
+            info_n = s.krow[k];
+            load_row<kFromHeads, LC>(a, b, info_n & 255, lane, fill, xn);
+            load_geo(info_n & 255, gn);
+        }
+        if (raw) {
+            if (write_back) {
+                float *wb = a.attn + ((size_t)b * L + p) * L + lane;
+#pragma unroll
+                for (int t = 0; t < LC; ++t)
+                    if (lane + kWarp * t < L && x[t] < a.clamp_e) wb[kWarp * t] = -INFINITY;              // :335
             }
-            if (raw) {
-                if (write_back) {
+            warp_softmax<LC>(x, a.clamp_e, use_clamp);
+        }
+        RCLK(5);
+        if (info & 0x10000) {          // first position of output row r1: plain stores
 #pragma unroll
-                    for (int t = 0; t < LC; ++t) {
-                        const int q = lane + kWarp * t;
-                        if (q < L && x[t] < a.clamp_e) a.attn[((size_t)b * L + p) * L + q] = -INFINITY;  // :335
-                    }
-                }
-                warp_softmax<LC>(x, L, lane, a.clamp_e, use_clamp);
-            }
-            __syncwarp();
-            if (k == k_begin) {
+            for (int t = 0; t < LC; ++t) { bufA[dst[t]] = x[t]; bufG[dst[t]] = g[t]; }
+        } else {                        // later positions: running sums continue; duplicates are parked again
 #pragma unroll
-                for (int t = 0; t < LC; ++t) {
-                    if (slot[t] >= 0) { if (slot[t] < kMaxL) { bufA[slot[t]] = x[t]; bufG[slot[t]] = g[t]; } }
-                    else { dupA[~slot[t]] = x[t]; dupG[~slot[t]] = g[t]; }
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < LC; ++t) {
-                    if (slot[t] >= 0) { if (slot[t] < kMaxL) { bufA[slot[t]] = bufA[slot[t]] + x[t]; bufG[slot[t]] = bufG[slot[t]] + g[t]; } }
-                    else { dupA[~slot[t]] = x[t]; dupG[~slot[t]] = g[t]; }
-                }
-            }
-            __syncwarp();
-            for (int m = lane; m < nmulti; m += kWarp) {     // fold the repeated codes' chains, ascending positions
-                const int r = s.multi[m];
-                const int base = s.start[r] - r, len = s.cnt[r] - 1;
-                float va = bufA[r], vg = bufG[r];
-                for (int kk = 0; kk < len; ++kk) { va = va + dupA[base + kk]; vg = vg + dupG[base + kk]; }
-                bufA[r] = va;
-                bufG[r] = vg;
+            for (int t = 0; t < LC; ++t) {
+                const bool dup = (dupmask >> t) & 1u;
+                const float oa = bufA[dst[t]], og = bufG[dst[t]];
+                bufA[dst[t]] = dup ? x[t] : oa + x[t];
+                bufG[dst[t]] = dup ? g[t] : og + g[t];
             }
         }
         __syncwarp();
+        if (has_m) {                    // fold the repeated codes' chains, ascending positions
+            float va = bufA[m_r], vg = bufG[m_r];
+            for (int kk = 0; kk < m_len; ++kk) { va = va + bufA[m_base + kk]; vg = vg + bufG[m_base + kk]; }
+            bufA[m_r] = va;
+            bufG[m_r] = vg;
+        }
+        for (int m = lane + kWarp; m < nmulti; m += kWarp) {
+            const int r = s.multi[m];
+            const int base = n + s.start[r] - r, len = s.cnt[r] - 1;
+            float va = bufA[r], vg = bufG[r];
+            for (int kk = 0; kk < len; ++kk) { va = va + bufA[base + kk]; vg = vg + bufG[base + kk]; }
+            bufA[r] = va;
+            bufG[r] = vg;
+        }
+        __syncwarp();
+        RCLK(6);
+        if (!(info & 0x20000)) continue;   // more positions of r1 follow
 
-        // epilogue: block mean, row normalisation, nan_to_num, 2->1 mix
+        // epilogue: block mean, row normalisation, nan_to_num, 2->1 mix.
         // block mean = sum / (cnt1 * cnt2) (utils.cpp:12) as a multiplication by the two precomputed reciprocals: at most
-        // 2 ulp from the reference's division (it is exactly 1.0 for the usual single-occurrence codes) and it keeps 14
-        // IEEE-division sequences per output row out of an issue-bound kernel
-        const float c1_inv = mean ? 1.0f / (float)(k_end - k_begin) : 1.0f;
+        // 2 ulp from the reference's division (exactly 1.0 for the usual single-occurrence codes)
+        const float c1_inv = s.cinvm[r1];
         float ea[LC], eg[LC];
         float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
         for (int t = 0; t < LC; ++t) {
-            const int r2 = lane + kWarp * t;
-            ea[t] = 0.0f; eg[t] = 0.0f;
-            if (t < nt && r2 < n) {
-                const float sc = mean ? c1_inv * cnt_inv[t] : 1.0f;
-                ea[t] = bufA[r2] * sc;
-                eg[t] = bufG[r2] * sc;
-                s0 += eg[t];
-                s1 += ea[t];
-            }
+            const float sc = c1_inv * s.cinvm[lane + kWarp * t];   // 0 for the slots >= n (duplicates, padding)
+            ea[t] = bufA[lane + kWarp * t] * sc;
+            eg[t] = bufG[lane + kWarp * t] * sc;
+            s0 += eg[t];
+            s1 += ea[t];
         }
+        __syncwarp();                   // the buffer is rewritten by the next row
         s0 = warp_sum(s0);
         s1 = warp_sum(s1);
-        // one reciprocal per row and channel (<= 1 ulp from x / s); a row whose sums are finite and non-zero has only
-        // finite entries, so nan_to_num (large_scale_feat_to_e.cpp:135) is only applied to the other rows
-        const float inv0 = 1.0f / s0, inv1 = 1.0f / s1;
-        const bool clean = isfinite(inv0) && isfinite(inv1) && isfinite(s0) && isfinite(s1);
-        float *o = a.edges + (size_t)b * L * L + (size_t)r1 * L;
+        float *o = a.edges + (size_t)b * L * L + (size_t)r1 * L + lane;
+        // a row whose sums are ordinary positive numbers has only finite entries: one reciprocal per channel (<= 1 ulp from
+        // x / s), folded with the mix weights; every other row takes the reference's division + nan_to_num
+        // (large_scale_feat_to_e.cpp:135) element by element
+        if (s0 > 1.0e-30f && s0 < 1.0e30f && s1 > 1.0e-30f && s1 < 1.0e30f) {
+            const float f0 = w0 * rcp_approx(s0), f1 = w1 * rcp_approx(s1);
 #pragma unroll
-        for (int t = 0; t < LC; ++t) {
-            const int r2 = lane + kWarp * t;
-            if (r2 < n) {
-                float v0 = eg[t] * inv0, v1 = ea[t] * inv1;
-                if (!clean) { v0 = nan_to_num0(v0); v1 = nan_to_num0(v1); }
-                o[r2] = v0 * w0 + v1 * w1;                     // :140
-            } else if (r2 < L && (a.flags & SH_G_ZERO_PAD)) {
-                o[r2] = 0.0f;                                  // match.py:54 padding, produced in place
-            }
+            for (int t = 0; t < LC; ++t)
+                if (lane + kWarp * t < n_store) o[kWarp * t] = eg[t] * f0 + ea[t] * f1;               // :140
+        } else {
+#pragma unroll
+            for (int t = 0; t < LC; ++t)
+                if (lane + kWarp * t < n_store)
+                    o[kWarp * t] = (lane + kWarp * t < n) ? nan_to_num0(eg[t] / s0) * w0 + nan_to_num0(ea[t] / s1) * w1 : 0.0f;
         }
-        r1 = r1_next;
+        RCLK(7);
     }
+#ifdef SH_GRAPH_CLOCKS
+    if (lane == 0) { atomicAdd(&g_clk[5], (unsigned long long)racc_[0]); atomicAdd(&g_clk[6], (unsigned long long)racc_[1]); atomicAdd(&g_clk[7], (unsigned long long)racc_[2]); }
+#endif
 }
 
-template <bool kFromHeads, int LC>
-__global__ void __launch_bounds__(kGraphThreads) instance_graph_kernel(GraphArgs a)
+// grid: (image, split) pairs; every CTA ranks the codes of its image and builds 1/nsplit of the edge rows (split 0 also
+// the vertices), so that B images spread evenly over the 148 SMs.
+template <bool kFromHeads, int LC, int kWarps>
+__global__ void __launch_bounds__(kWarps * kWarp, kWarps == 8 ? 3 : 2) instance_graph_kernel(GraphArgs a, int nsplit)
 {
-    __shared__ GraphSmem s;
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    __shared__ GraphSmemT<kWarps> s;
+    for (int u = blockIdx.x; u < a.B * nsplit; u += gridDim.x) {
+        const int b = u / nsplit, split = u % nsplit;
+        // the cls row is requested before the (latency-bound) ranking, into warp 0's registers
+#ifdef SH_GRAPH_CLOCKS
+        long long t_ = clock64();
+#endif
+        float cls[LC];
+        const bool do_vertices = a.vertex_w && split == 0;
+        if (do_vertices && threadIdx.x < kWarp) load_cls_row<kFromHeads, LC>(a, b, cls);
         rank_codes(s, a.ingredients + (size_t)b * a.L, a.L);
-        if (threadIdx.x == 0) {
-            if (a.num_vertices) a.num_vertices[b] = s.n;
-            if (a.max_vertices) atomicMax(a.max_vertices, s.n);
+        CLK(0);
+        const int n = s.n;
+        if (threadIdx.x == 0 && split == 0) {
+            if (a.num_vertices) a.num_vertices[b] = n;
+            if (a.max_vertices) atomicMax(a.max_vertices, n);
         }
-        if (a.vertex_w) build_vertices<kFromHeads, LC>(a, s, b);
+        if (do_vertices) build_vertices<kFromHeads, LC>(a, s, b, cls);
+        CLK(1);
         if (a.edges) {
-            build_edges_scatter<kFromHeads, LC>(a, s, b);
+            if (threadIdx.x < kMaxL)
+                s.cinvm[threadIdx.x] = (int)threadIdx.x < n ? ((a.flags & SH_G_SUM) ? 1.0f : 1.0f / (float)s.cnt[threadIdx.x]) : 0.0f;
+            if (threadIdx.x < a.L) {   // CSR entry -> position | rank << 8 | first-of-row << 16 | last-of-row << 17
+                const int p = s.pos[threadIdx.x], r = s.rank[p];
+                s.krow[threadIdx.x] = p | (r << 8) | (threadIdx.x == s.start[r] ? 0x10000 : 0) |
+                                      (threadIdx.x + 1 == s.start[r + 1] ? 0x20000 : 0);
+            }
+            __syncthreads();
+            CLK(2);
+            build_edges_scatter<kFromHeads, LC>(a, s, b, split, nsplit);
+            CLK(3);
             if (a.flags & SH_G_ZERO_PAD) {   // rows n..L-1 of the [L, L] slot
                 float *o = a.edges + (size_t)b * a.L * a.L;
-                for (int i = s.n * a.L + threadIdx.x; i < a.L * a.L; i += blockDim.x) o[i] = 0.0f;
+                for (int i = n * a.L + split * blockDim.x + threadIdx.x; i < a.L * a.L; i += blockDim.x * nsplit) o[i] = 0.0f;
             }
         }
         __syncthreads();
+        CLK(4);
     }
 }
 
@@ -647,13 +786,41 @@ extern "C" int sh_dev_instance_graphs(const int64_t *ingredients, float *attn, f
     a.B = B; a.L = L; a.H = H; a.clamp_v = clamp_vertex; a.clamp_e = clamp_edge;
     a.w_v = w_vertex; a.w_e = w_edge; a.flags = flags;
     a.ids = ids; a.vertex_w = vertex_w; a.edges = edges; a.num_vertices = num_vertices; a.max_vertices = max_vertices;
-    const int grid = B;
+    // (image, split) CTAs.  A CTA's fixed part (rank the codes, vertices, per-lane constants) is ~1/5 of an image, and
+    // r01 measurements at B = 256 (profiles/r01_graph_variants.md) have 1 split fastest once every SM has a CTA; smaller
+    // batches are split so that no SM idles.
+    int nsplit = 1;
+    if (edges) {
+        static const int forced = [] { const char *e = getenv("SCHEMANET_GRAPH_SPLIT"); return e ? atoi(e) : 0; }();
+        nsplit = forced > 0 ? forced : (int)max((int64_t)1, min((int64_t)4, ceil_div64((int64_t)sm_count(), B)));
+    }
+    const int grid = B * nsplit;
     cudaStream_t st = (cudaStream_t)stream;
     const bool narrow = L <= 7 * kWarp;   // 196 tokens: 7 columns per lane instead of 8
-    if (heads && narrow) SH_LAUNCH("instance_graph_kernel", st, instance_graph_kernel<true, 7><<<grid, kGraphThreads, 0, st>>>(a));
-    else if (heads) SH_LAUNCH("instance_graph_kernel", st, instance_graph_kernel<true, 8><<<grid, kGraphThreads, 0, st>>>(a));
-    else if (narrow) SH_LAUNCH("instance_graph_kernel", st, instance_graph_kernel<false, 7><<<grid, kGraphThreads, 0, st>>>(a));
-    else SH_LAUNCH("instance_graph_kernel", st, instance_graph_kernel<false, 8><<<grid, kGraphThreads, 0, st>>>(a));
+    // 12 warps per image, two CTAs per SM at 80 registers (r01: 8 warps x 3 CTAs is ~4-12 % slower, 16 warps at 64
+    // registers spills and is ~25 % slower; profiles/r01_graph_variants.md).  SCHEMANET_GRAPH_WARPS=8 selects the former.
+    static const int warps = [] { const char *e = getenv("SCHEMANET_GRAPH_WARPS"); return e ? atoi(e) : 12; }();
+#define SH_GRAPH_LAUNCH(HEADS, LCOLS, W)                                                                                \
+    SH_LAUNCH("instance_graph_kernel", st, instance_graph_kernel<HEADS, LCOLS, W><<<grid, W * kWarp, 0, st>>>(a, nsplit))
+#define SH_GRAPH_LAUNCH_OCC(HEADS, LCOLS)                                                                               \
+    do {                                                                                                                \
+        if (warps == 8) SH_GRAPH_LAUNCH(HEADS, LCOLS, 8);                                                               \
+        else SH_GRAPH_LAUNCH(HEADS, LCOLS, 12);                                                                         \
+    } while (0)
+    if (heads && narrow) SH_GRAPH_LAUNCH_OCC(true, 7);
+    else if (heads) SH_GRAPH_LAUNCH_OCC(true, 8);
+    else if (narrow) SH_GRAPH_LAUNCH_OCC(false, 7);
+    else SH_GRAPH_LAUNCH_OCC(false, 8);
+#ifdef SH_GRAPH_CLOCKS
+    {
+        unsigned long long h[8];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_clk, sizeof(h));
+        fprintf(stderr, "graph clocks (warp-sum): rank %llu vert %llu setup %llu rows %llu tail %llu | softmax %llu scatter+fold %llu epilogue %llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+        unsigned long long z[8] = {};
+        cudaMemcpyToSymbol(g_clk, z, sizeof(z));
+    }
+#endif
     SH_CHECK_LAUNCH();
     return 0;
 }

@@ -175,6 +175,42 @@ def test_golden_cpp_extension_dropin(device):
     assert wg.grad is not None and wg.grad.abs().sum() > 0
 
 
+def test_instance_graphs_wide_codes_take_the_same_path_result():
+    """Codes outside [0, 2^23) (negative, > 2^40) are ranked by the 64-bit sort: an order-preserving relabelling of
+    the codes must give bit-identical graphs (only the ids change), for the hot kernel and the init-time APIs."""
+    from schemanet_b200 import native
+    g = torch.Generator().manual_seed(5)
+    B, L, M = 6, 196, 300
+    ing = torch.randint(0, M, (B, L), generator=g)
+    ing[1] = 7                       # one code everywhere
+    ing[2] = torch.arange(L)         # all distinct
+    wide = ing * (1 << 33) - (1 << 50)
+    attn = (0.5 * torch.randn(B, L, L, generator=g)).cuda()
+    cls = (0.5 * torch.randn(B, L, generator=g)).cuda()
+    geo = ho.pair_wise_point_sim(14, 14, 1.0, 2.0).cuda()
+    w = torch.tensor([0.3, 0.7]).cuda()
+    a = native.instance_graphs(ing.cuda(), attn.clone(), cls.clone(), geo, w, w, -1.0, -1.0, zero_pad=True)
+    b = native.instance_graphs(wide.cuda(), attn.clone(), cls.clone(), geo, w, w, -1.0, -1.0, zero_pad=True)
+    assert torch.equal(a.num_vertices, b.num_vertices)
+    nv = a.num_vertices.tolist()
+    assert nv[1] == 1 and nv[2] == L
+    for i, n in enumerate(nv):
+        assert torch.equal(a.ids[i, :n] * (1 << 33) - (1 << 50), b.ids[i, :n])
+        assert torch.equal(a.vertex_w[i, :n], b.vertex_w[i, :n])
+    assert torch.equal(a.edges, b.edges)
+    # and the 64-bit path against the oracle
+    wcol = torch.tensor([[0.3], [0.7]])
+    eb = b.edges.view(B, L, L)
+    ref = ho.instance_graphs(wide, attn.cpu(), cls.cpu(), wcol, wcol, clamp_vertex=-1.0, clamp_edge=-1.0)
+    for i, n in enumerate(nv):
+        assert torch.equal(b.ids[i, :n].cpu(), ref["instance_ingredients"][i])
+        rel_close(b.vertex_w[i, :n], ref["instance_vertices"][i], what="vertices (wide codes)")
+        e = eb[i, :n, :n].cpu()
+        assert torch.equal(e == 0, ref["instance_edges"][i] == 0)
+        rel_close(e, ref["instance_edges"][i], what="edges (wide codes)")
+        assert eb[i, n:].abs().sum() == 0 and eb[i, :, n:].abs().sum() == 0
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # seeded inputs vs the oracle
 # ----------------------------------------------------------------------------------------------------------------
