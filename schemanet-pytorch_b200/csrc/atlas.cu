@@ -43,7 +43,7 @@ class_vertices_kernel(const float *__restrict__ vw, int K, int Vc, float *__rest
 template <int kChunks>
 __global__ void __launch_bounds__(256)
 class_edges_fast_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, int Vc, float thr, int prune,
-                        int prune_in_place, int remove_self_loop, float *__restrict__ ce)
+                        int prune_in_place, int remove_self_loop, float *__restrict__ ce, float *__restrict__ rowinv)
 {
     constexpr int RUN = 8;
     const int lane = threadIdx.x & 31;
@@ -68,7 +68,7 @@ class_edges_fast_kernel(float *__restrict__ ew, const float *__restrict__ cv, in
         }
         float4 cur[kChunks], nxt[kChunks];
         float *src = ew + ((size_t)k * Vc + i0) * Vc;
-        float *dst = ce + ((size_t)k * Vc + i0) * Vc;
+        float *dst = ce ? ce + ((size_t)k * Vc + i0) * Vc : nullptr;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
             const int j = (c * kWarp + lane) * 4;
@@ -113,6 +113,10 @@ class_edges_fast_kernel(float *__restrict__ ew, const float *__restrict__ cv, in
             // reference: emit zeros.  Only non-finite sums need the element-wise nan_to_num.
             const bool ordinary = acc < INFINITY && acc >= 0.0f;
             const float inv = (acc == 0.0f) ? 0.0f : 1.0f / acc;
+            // rowinv: everything a consumer needs to rebuild this row of class_edges from the (pruned) parameter:
+            // ce[i][j] = nan_to_num(max(ew[i][j], 0) * rowinv[i]) -- bit-identical to the values stored below
+            if (rowinv && lane == 0) rowinv[(size_t)k * Vc + i] = inv;
+            if (dst == nullptr) continue;
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 const int j = (c * kWarp + lane) * 4;
@@ -132,7 +136,7 @@ class_edges_fast_kernel(float *__restrict__ ew, const float *__restrict__ cv, in
 // Generic path: any Vc / alignment, two passes over the row (the second one hits L1/L2).
 __global__ void __launch_bounds__(256)
 class_edges_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, int Vc, float thr, int prune,
-                   int prune_in_place, int remove_self_loop, float *__restrict__ ce)
+                   int prune_in_place, int remove_self_loop, float *__restrict__ ce, float *__restrict__ rowinv)
 {
     const int lane = threadIdx.x & 31;
     const int64_t rows = (int64_t)K * Vc;
@@ -140,7 +144,7 @@ class_edges_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, 
     for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
         const int k = (int)(row / Vc), i = (int)(row % Vc);
         float *src = ew + row * Vc;
-        float *dst = ce + row * Vc;
+        float *dst = ce ? ce + row * Vc : nullptr;
         const float *cvk = cv + (size_t)k * Vc;
         const bool keep_i = !prune || cvk[i] > thr;
         float acc = 0.0f;
@@ -154,6 +158,8 @@ class_edges_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, 
         }
         acc = warp_sum(acc);
         const float inv = 1.0f / acc;
+        if (rowinv && lane == 0) rowinv[row] = inv;
+        if (dst == nullptr) continue;
         for (int j = lane; j < Vc; j += kWarp) {
             float x = src[j];   // pruned entries were just zeroed in place or are re-masked here
             if (prune && !(keep_i && cvk[j] > thr)) x = 0.f;
@@ -168,15 +174,20 @@ class_edges_kernel(float *__restrict__ ew, const float *__restrict__ cv, int K, 
 
 using namespace sh;
 
-extern "C" int sh_dev_class_atlas(const float *vertex_weights, float *edge_weights, int K, int Vc, float prune_threshold,
-                                  int prune_in_place, int remove_self_loop, float *class_vertices, float *class_edges,
-                                  sh_stream_t stream)
+namespace sh {
+
+int launch_class_vertices(const float *vertex_weights, int K, int Vc, float *class_vertices, cudaStream_t st)
 {
-    SH_REQUIRE(K > 0 && Vc > 0, "class_atlas: bad shape K=%d Vc=%d", K, Vc);
-    cudaStream_t st = (cudaStream_t)stream;
     SH_LAUNCH("class_vertices_kernel", st, class_vertices_kernel<<<K, 256, 0, st>>>(vertex_weights, K, Vc, class_vertices));
     SH_CHECK_LAUNCH();
-    if (class_edges == nullptr) return 0;
+    return 0;
+}
+
+// One pass over the edge parameter: in-place prune, class_edges [K, Vc, Vc] (may be null: not materialised) and/or the
+// per-row normalisers rowinv [K, Vc] (may be null) from which a consumer rebuilds any class_edges entry exactly.
+int launch_class_edges(float *edge_weights, const float *class_vertices, int K, int Vc, float prune_threshold,
+                       int prune_in_place, int remove_self_loop, float *class_edges, float *rowinv, cudaStream_t st)
+{
     const int prune = prune_threshold >= 0.0f ? 1 : 0;
     const int64_t rows = (int64_t)K * Vc;
     const bool aligned = (Vc % 8 == 0) && ((reinterpret_cast<uintptr_t>(edge_weights) | reinterpret_cast<uintptr_t>(class_edges) |
@@ -185,15 +196,29 @@ extern "C" int sh_dev_class_atlas(const float *vertex_weights, float *edge_weigh
         const int grid = (int)min(ceil_div64(rows / 8, 8), (int64_t)sm_count() * 16);
         if (Vc <= 512)
             SH_LAUNCH("class_edges_kernel", st, class_edges_fast_kernel<4><<<grid, 256, 0, st>>>(edge_weights, class_vertices, K, Vc, prune_threshold, prune,
-                                                        prune_in_place, remove_self_loop, class_edges));
+                                                        prune_in_place, remove_self_loop, class_edges, rowinv));
         else
             SH_LAUNCH("class_edges_kernel", st, class_edges_fast_kernel<8><<<grid, 256, 0, st>>>(edge_weights, class_vertices, K, Vc, prune_threshold, prune,
-                                                        prune_in_place, remove_self_loop, class_edges));
+                                                        prune_in_place, remove_self_loop, class_edges, rowinv));
     } else {
         const int grid = (int)min(ceil_div64(rows, 8), (int64_t)sm_count() * 32);
         SH_LAUNCH("class_edges_kernel", st, class_edges_kernel<<<grid, 256, 0, st>>>(edge_weights, class_vertices, K, Vc, prune_threshold, prune,
-                                                    prune_in_place, remove_self_loop, class_edges));
+                                                    prune_in_place, remove_self_loop, class_edges, rowinv));
     }
     SH_CHECK_LAUNCH();
     return 0;
+}
+
+}  // namespace sh
+
+extern "C" int sh_dev_class_atlas(const float *vertex_weights, float *edge_weights, int K, int Vc, float prune_threshold,
+                                  int prune_in_place, int remove_self_loop, float *class_vertices, float *class_edges,
+                                  sh_stream_t stream)
+{
+    SH_REQUIRE(K > 0 && Vc > 0, "class_atlas: bad shape K=%d Vc=%d", K, Vc);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (launch_class_vertices(vertex_weights, K, Vc, class_vertices, st)) return 1;
+    if (class_edges == nullptr) return 0;
+    return launch_class_edges(edge_weights, class_vertices, K, Vc, prune_threshold, prune_in_place, remove_self_loop,
+                              class_edges, nullptr, st);
 }

@@ -398,13 +398,29 @@ extern "C" int sh_dev_class_side(const sh_gnn_params *p, const float *vertex_wei
                                  int prune_in_place, int remove_self_loop, float *class_vertices, float *class_edges,
                                  float *feat_class, void *workspace, size_t workspace_bytes, sh_stream_t stream)
 {
-    SH_REQUIRE(p && K > 0 && Vc > 0 && class_vertices && class_edges && feat_class, "class_side: bad arguments");
+    SH_REQUIRE(p && K > 0 && Vc > 0 && class_vertices && feat_class, "class_side: bad arguments");
     const int D = p->embed_dim;
     SH_REQUIRE(workspace_bytes >= sh_class_side_workspace_bytes(K, Vc, D), "class_side: workspace too small");
-    if (sh_dev_class_atlas(vertex_weights, edge_weights, K, Vc, prune_threshold, prune_in_place, remove_self_loop,
-                           class_vertices, class_edges, stream)) return 1;
-    return sh_dev_gnn_forward_class(p, K, Vc, class_vertices, class_edges, class_ingredients, prune_threshold, feat_class,
-                                    workspace, workspace_bytes, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tensor_path = gnn_tc_supported(D, Vc) && getenv("SCHEMANET_GNN_SIMT") == nullptr;
+    if (!tensor_path || getenv("SCHEMANET_CLASS_UNFUSED") != nullptr) {
+        SH_REQUIRE(class_edges != nullptr, "class_side: class_edges may only be omitted on the tensor-core path "
+                                           "(embed_dim %% 256 == 0, embed_dim <= 1024, Vc >= 32)");
+        if (sh_dev_class_atlas(vertex_weights, edge_weights, K, Vc, prune_threshold, prune_in_place, remove_self_loop,
+                               class_vertices, class_edges, stream)) return 1;
+        return sh_dev_gnn_forward_class(p, K, Vc, class_vertices, class_edges, class_ingredients, prune_threshold, feat_class,
+                                        workspace, workspace_bytes, stream);
+    }
+    if (launch_class_vertices(vertex_weights, K, Vc, class_vertices, st)) return 1;
+    const size_t slab = align_up((size_t)K * Vc * D * sizeof(float), 256);
+    const int chunks = pool_chunks(Vc);
+    char *ws = (char *)workspace;
+    float *partial = (float *)(ws + 2 * slab);
+    char *tc_ws = ws + 2 * slab + align_up((size_t)K * chunks * D * sizeof(float), 256) + align_up((size_t)K * D * sizeof(float), 256);
+    if (gnn_class_side_tc(p, edge_weights, K, Vc, prune_threshold, prune_in_place, remove_self_loop, class_vertices, class_edges,
+                          class_ingredients, chunks, partial, tc_ws, st))
+        return 1;
+    return launch_pool_fc(p, partial, K, chunks, Vc, nullptr, feat_class, st);
 }
 
 // GNN.forward on the K class graphs produced by get_atlas(): like sh_dev_gnn_forward, but knows that vertices with

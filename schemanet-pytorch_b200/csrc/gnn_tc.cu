@@ -565,6 +565,147 @@ class_adj_prep_kernel(const float *__restrict__ ce, int K, int Vc, int ldk, int 
     }
 }
 
+// Same output as class_adj_prep_kernel without a materialised class_edges tensor: entry (i, j) of class_edges is rebuilt
+// from the (pruned) edge parameter and the per-row normalisers the atlas pass left in rowinv,
+//   ce[i][j] = nan_to_num(max(ew[i][j], 0) * rowinv[i]),  0 on the diagonal when self loops are removed
+// (bit-identical to what class_edges_*_kernel would have stored).  (E + E^T) / 2 is symmetric: a WARP owns the pair of
+// 32x32 tiles (I, J) and (J, I), I <= J, gathers both source tiles once (8 independent loads per lane in flight, row
+// indices and normalisers passed around by shuffle) and writes both results.  A fixed number of CTAs per class walks
+// that class's work list (tile pairs of the active corner, then the identity / zero padding tiles the GEMM reads), so no
+// CTA is launched just to exit.
+constexpr int kAdjWarps = 4;
+constexpr int kAdjBatch = 16;   // gathered loads a lane keeps in flight (the kernel is bound by DRAM latency)
+
+// One 32-row strip of padding: columns [c0, c1) of rows [pi0, pi0 + 32) get the identity / zero pattern.
+__device__ __forceinline__ void adj_fill_strip(float *__restrict__ adj_hi, float *__restrict__ adj_lo, size_t base, int ldk,
+                                               int Vc, int pi0, int c0, int c1, int lane)
+{
+    c1 = min(c1, ldk);
+    const int rows = min(32, Vc - pi0);
+    for (int pj = c0 + lane; pj < c1; pj += 32) {
+        float *ph = adj_hi + base + (size_t)pi0 * ldk + pj, *pl = adj_lo + base + (size_t)pi0 * ldk + pj;
+        const int diag = pj - pi0;          // row of this strip that holds the 1 of column pj
+        for (int r = 0; r < rows; ++r) {
+            *ph = (r == diag) ? 1.0f : 0.0f;
+            *pl = 0.0f;
+            ph += ldk;
+            pl += ldk;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kAdjWarps * 32)
+class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ rowinv, int K, int Vc, int ldk, int unit_rows,
+                     int remove_self_loop, const int32_t *__restrict__ n_act, const int32_t *__restrict__ old_of_new,
+                     float *__restrict__ adj_hi, float *__restrict__ adj_lo, int ctas_per_class)
+{
+    __shared__ float tiles[kAdjWarps][2][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // last classes first: their edge parameters are what the atlas pass, which ran just before, left in L2
+    const int k = K - 1 - blockIdx.x / ctas_per_class;
+    const int wid = (blockIdx.x % ctas_per_class) * kAdjWarps + warp, nw = ctas_per_class * kAdjWarps;
+    const int nA = n_act[k];
+    const int rowsA = min(Vc, (nA + unit_rows - 1) / unit_rows * unit_rows), colsA = (nA + G_BK - 1) / G_BK * G_BK;
+    const int nt = (nA + 31) / 32, pairs = nt * (nt + 1) / 2;
+    const int TR = (Vc + 31) / 32;
+    const size_t base = (size_t)k * Vc * ldk;
+    const float *ewk = ew + (size_t)k * Vc * Vc;
+    const float *rik = rowinv + (size_t)k * Vc;
+    const int32_t *old = old_of_new + (size_t)k * Vc;
+    float (*T)[33] = tiles[warp][0];
+    float (*S)[33] = tiles[warp][1];
+    // work list of the class: tile pairs of the active corner first (the expensive items), then one item per 32-row strip
+    // of padding
+    for (int item = wid; item < pairs + TR; item += nw) {
+        if (item >= pairs) {
+            const int pi0 = (item - pairs) * 32;
+            const int act_end = pi0 < nA ? nt * 32 : 0;                 // columns [0, act_end) belong to tile pairs
+            const int a_end = pi0 < rowsA ? colsA : 0;                  // region A: the active corner up to the tile edges
+            if (a_end > act_end) adj_fill_strip(adj_hi, adj_lo, base, ldk, Vc, pi0, act_end, a_end, lane);
+            const int ub = pi0 / unit_rows;                             // region B: diagonal blocks with inactive vertices
+            if ((ub + 1) * unit_rows > nA) {
+                const int b0 = max(ub * unit_rows, max(act_end, a_end)), b1 = (ub + 1) * unit_rows;
+                if (b1 > b0) adj_fill_strip(adj_hi, adj_lo, base, ldk, Vc, pi0, b0, b1, lane);
+            }
+            continue;
+        }
+        // item -> (I, J), I <= J: item = J (J + 1) / 2 + I
+        int J = (int)((sqrtf(8.0f * (float)item + 1.0f) - 1.0f) * 0.5f);
+        while ((J + 1) * (J + 2) / 2 <= item) ++J;
+        while (J * (J + 1) / 2 > item) --J;
+        const int I = item - J * (J + 1) / 2;
+        const int pi0 = I * 32, pj0 = J * 32;
+        // lanes past the active corner read element 0 of the class with a zero normaliser: their values become exact zeros
+        const bool vi = pi0 + lane < nA, vj = pj0 + lane < nA;
+        const int oi = vi ? old[pi0 + lane] : 0, oj = vj ? old[pj0 + lane] : 0;
+        const float si = vi ? __ldg(rik + oi) : 0.0f, sj = vj ? __ldg(rik + oj) : 0.0f;
+        const float *col_i = ewk + oi, *col_j = ewk + oj;
+        const int nvi = min(32, nA - pi0), nvj = min(32, nA - pj0);   // valid rows of the two source tiles
+        // rows whose normaliser is not an ordinary positive number (empty, infinite or NaN row sums) need nan_to_num
+        const bool special = __any_sync(kFull, (vi && !(si > 0.0f && si <= FLT_MAX)) || (vj && !(sj > 0.0f && sj <= FLT_MAX)));
+        // source tile of the mirror: T[r][lane] = ce[old_j(r)][old_i(lane)]
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += kAdjBatch) {
+            float v[kAdjBatch];
+#pragma unroll
+            for (int u = 0; u < kAdjBatch; ++u) v[u] = __ldg(col_i + (size_t)__shfl_sync(kFull, oj, rb + u) * Vc);
+#pragma unroll
+            for (int u = 0; u < kAdjBatch; ++u) {
+                float e = fmaxf(v[u], 0.0f) * __shfl_sync(kFull, sj, rb + u);
+                if (!vi || rb + u >= nvj) e = 0.0f;
+                if (special) e = nan_to_num0(e);
+                if (remove_self_loop && __shfl_sync(kFull, oj, rb + u) == oi) e = 0.0f;
+                T[rb + u][lane] = e;
+            }
+        }
+        __syncwarp();
+        // this tile: S[r][lane] = (ce[old_i(r)][old_j(lane)] + ce[old_j(lane)][old_i(r)]) / 2 + identity
+        const bool col_ok = pj0 + lane < ldk;
+        float *ph = adj_hi + base + (size_t)pi0 * ldk + pj0 + lane, *pl = adj_lo + base + (size_t)pi0 * ldk + pj0 + lane;
+        const int diag = (I == J) ? lane : -1;
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += kAdjBatch) {
+            float v[kAdjBatch];
+#pragma unroll
+            for (int u = 0; u < kAdjBatch; ++u) v[u] = __ldg(col_j + (size_t)__shfl_sync(kFull, oi, rb + u) * Vc);
+#pragma unroll
+            for (int u = 0; u < kAdjBatch; ++u) {
+                const int r = rb + u;
+                float e = fmaxf(v[u], 0.0f) * __shfl_sync(kFull, si, r);
+                if (!vj || r >= nvi) e = 0.0f;
+                if (special) e = nan_to_num0(e);
+                if (remove_self_loop && __shfl_sync(kFull, oi, r) == oj) e = 0.0f;
+                const float sym = (e + T[lane][r]) / 2.0f + ((r == diag) ? 1.0f : 0.0f);
+                S[r][lane] = sym;
+                if (col_ok && pi0 + r < Vc) {
+                    float h, l;
+                    split_tf32(sym, h, l);
+                    *ph = h;
+                    *pl = l;
+                }
+                ph += ldk;
+                pl += ldk;
+            }
+        }
+        __syncwarp();
+        if (I != J && pi0 + lane < ldk) {
+            ph = adj_hi + base + (size_t)pj0 * ldk + pi0 + lane;       // mirror tile (J, I)
+            pl = adj_lo + base + (size_t)pj0 * ldk + pi0 + lane;
+            const int rows = min(32, Vc - pj0);
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) {
+                float h, l;
+                split_tf32(S[lane][r], h, l);
+                *ph = h;
+                *pl = l;
+                ph += ldk;
+                pl += ldk;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------------
@@ -625,6 +766,7 @@ bool gnn_tc_supported(int D, int n_fixed)
 struct TcBuffers {
     float *adj_hi, *adj_lo, *xt_hi, *xt_lo, *xt2_hi, *xt2_lo, *y_hi, *y_lo, *w_hi, *w_lo, *h_rows;
     int32_t *n_act, *old_of_new;
+    float *rowinv;
     int64_t *pid;
     float *pvw;
     int ldk;
@@ -652,6 +794,7 @@ static TcBuffers carve_tc(void *base, int G, int n_fixed, int D)
     b.h_rows = (float *)(p + off); off += y_b;
     b.n_act = (int32_t *)(p + off); off += al256((size_t)G * 4);
     b.old_of_new = (int32_t *)(p + off); off += al256((size_t)G * n_fixed * 4);
+    b.rowinv = (float *)(p + off); off += al256((size_t)G * n_fixed * 4);
     b.pid = (int64_t *)(p + off); off += al256((size_t)G * n_fixed * 8);
     b.pvw = (float *)(p + off); off += al256((size_t)G * n_fixed * 4);
     b.bytes = off;
@@ -857,6 +1000,39 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
               class_adj_prep_kernel<<<dim3(ceil_div(b.ldk, 32), ceil_div(Vc, 32), K), 256, 0, st>>>(
                   class_edges, K, Vc, b.ldk, G_BM * gemm_ctas(), b.n_act, b.old_of_new, b.adj_hi, b.adj_lo));
     SH_CHECK_LAUNCH();
+    return run_layers_tc(p, K, Vc, b.n_act, 1, nullptr, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st);
+}
+
+// Stage 3a + class side fused (sh_dev_class_side on the tensor-core path): the atlas pass leaves the per-row normalisers,
+// and the adjacency operand of the un-pruned vertices is gathered from the (pruned) edge parameter itself, so the full
+// [K, Vc, Vc] class_edges tensor is only written when the caller asks for it (class_edges != null) and never read back.
+int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc, float prune_threshold, int prune_in_place,
+                      int remove_self_loop, const float *class_vertices, float *class_edges,
+                      const int64_t *class_ingredients, int chunks, float *partial, void *workspace, cudaStream_t st)
+{
+    TcBuffers b = carve_tc(workspace, K, Vc, p->embed_dim);
+    SH_REQUIRE(Vc <= 65535, "class side: Vc too large");
+    const int prune = prune_threshold >= 0.0f ? 1 : 0;
+    SH_LAUNCH("class_perm_kernel", st,
+              class_perm_kernel<<<K, 1024, 0, st>>>(class_vertices, class_ingredients, Vc, prune_threshold, prune, b.n_act,
+                                                    b.old_of_new, b.pid, b.pvw));
+    SH_CHECK_LAUNCH();
+    if (launch_class_edges(edge_weights, class_vertices, K, Vc, prune_threshold, prune_in_place, remove_self_loop, class_edges,
+                           b.rowinv, st))
+        return 1;
+    {
+        // a few tile pairs per warp for the largest work list (all vertices active: TR (TR + 1) / 2 pairs); r01 sweep at
+        // K = 100, Vc = 1024: 12 CTAs/class 0.143 ms, 24: 0.133, 48: 0.122, 96: 0.123
+        const int tr = ceil_div(Vc, 32);
+        static const int forced = [] { const char *e = getenv("SCHEMANET_ADJ_CTAS"); return e ? atoi(e) : 0; }();
+        int cpc = max(4, min(64, ceil_div(tr * (tr + 1) / 2, kAdjWarps * 2)));
+        if (forced > 0) cpc = forced;
+        SH_LAUNCH("class_adj_prep_kernel", st,
+                  class_adj_raw_kernel<<<K * cpc, kAdjWarps * 32, 0, st>>>(edge_weights, b.rowinv, K, Vc, b.ldk, G_BM * gemm_ctas(),
+                                                                           remove_self_loop, b.n_act, b.old_of_new, b.adj_hi,
+                                                                           b.adj_lo, cpc));
+        SH_CHECK_LAUNCH();
+    }
     return run_layers_tc(p, K, Vc, b.n_act, 1, nullptr, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st);
 }
 

@@ -16,6 +16,16 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
                          const int64_t *class_ingredients, float prune_threshold, int chunks, float *partial,
                          void *workspace, cudaStream_t st);
 
+// sh_dev_class_side on the tensor-core path: atlas edges + class-graph GNN with the un-pruned vertices compacted on the fly
+int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc, float prune_threshold, int prune_in_place,
+                      int remove_self_loop, const float *class_vertices, float *class_edges,
+                      const int64_t *class_ingredients, int chunks, float *partial, void *workspace, cudaStream_t st);
+
+// atlas.cu
+int launch_class_vertices(const float *vertex_weights, int K, int Vc, float *class_vertices, cudaStream_t st);
+int launch_class_edges(float *edge_weights, const float *class_vertices, int K, int Vc, float prune_threshold,
+                       int prune_in_place, int remove_self_loop, float *class_edges, float *rowinv, cudaStream_t st);
+
 // out[rows, D] = A[rows, D] W^T with W [D, D] (fp32 CUDA-core GEMM from gnn.cu; used for the embedding-table shortcut)
 int launch_rows_linear(const float *A, const float *W, int rows, int D, float *out, cudaStream_t st);
 

@@ -318,9 +318,17 @@ def gnn_forward(params, G, n_fixed, sizes, ids, vertex_w, ld_v, edges, edge_batc
     return out
 
 
+def gnn_tensor_path(embed_dim: int, n_fixed: int) -> bool:
+    """Mirror of gnn_tc_supported() (csrc/gnn_tc.cu) plus the debugging overrides: does the GNN run on tcgen05?"""
+    return (embed_dim % 256 == 0 and embed_dim <= 1024 and n_fixed >= 32
+            and "SCHEMANET_GNN_SIMT" not in os.environ and "SCHEMANET_CLASS_UNFUSED" not in os.environ)
+
+
 def class_side(params, vertex_weights, edge_weights, class_ingredients, prune_threshold=None, prune_in_place=True,
-               remove_self_loop=False, out=None):
-    """get_atlas() + GNN(class graphs) in one call -> (class_vertices, class_edges, feat_class [K, D])."""
+               remove_self_loop=False, out=None, want_edges=True):
+    """get_atlas() + GNN(class graphs) in one call -> (class_vertices, class_edges, feat_class [K, D]).
+    want_edges=False (tensor-core path only): the [K, Vc, Vc] class_edges tensor is not materialised (returned as None);
+    the normalised edges of the un-pruned vertices go straight into the GNN's adjacency operand."""
     require_cuda(vertex_weights, edge_weights, class_ingredients)
     K, Vc = vertex_weights.shape
     vw = _f32c(vertex_weights.detach())
@@ -328,13 +336,16 @@ def class_side(params, vertex_weights, edge_weights, class_ingredients, prune_th
     if ew.dtype != torch.float32 or not ew.is_contiguous():
         raise RuntimeError("edge_weights must be a contiguous float32 CUDA tensor")
     ci = _i64c(class_ingredients)
+    if tuple(ci.shape) != (K, Vc) or tuple(ew.shape) != (K, Vc, Vc):
+        raise RuntimeError(f"class_side: class_ingredients {tuple(ci.shape)} / edge_weights {tuple(ew.shape)} do not match "
+                           f"vertex_weights {(K, Vc)}")
     D = params.embed_dim
     if out is None:
         cv = torch.empty(K, Vc, dtype=torch.float32, device=vw.device)
-        ce = torch.empty(K, Vc, Vc, dtype=torch.float32, device=vw.device)
+        ce = torch.empty(K, Vc, Vc, dtype=torch.float32, device=vw.device) if want_edges else None
         fk = torch.empty(K, D, dtype=torch.float32, device=vw.device)
     else:
-        cv, ce, fk = out                 # caller-owned buffers (no allocation on this call)
+        cv, ce, fk = out                 # caller-owned buffers (no allocation on this call); ce may be None
     ws = _workspace("class", lib().sh_class_side_workspace_bytes(K, Vc, D), vw.device)
     thr = -1.0 if prune_threshold is None else float(prune_threshold)
     check(lib().sh_dev_class_side(ctypes.byref(params.struct), ptr(vw), ptr(ew), ptr(ci), K, Vc, thr, int(prune_in_place),

@@ -358,6 +358,35 @@ def test_class_side_large_tile_path():
     rel_close(got, ho.gnn_forward(params, nodes, edges, ids, None), what="gnn class side")
 
 
+@pytest.mark.parametrize("K,Vc,D,thr,rsl", [(4, 1024, 256, 0.001, False), (3, 500, 256, 0.001, True), (2, 296, 512, 0.0034, False),
+                                            (3, 264, 256, None, False), (2, 301, 256, 0.0033, False)])
+def test_class_side_fused_equals_atlas_then_gnn(K, Vc, D, thr, rsl):
+    """sh_dev_class_side on the tensor-core path feeds the compacted, normalised edges straight into the adjacency
+    operand.  It must return bit-identical class embeddings whether or not the full class_edges tensor is asked for,
+    the same tensors as sh_dev_class_atlas followed by sh_dev_gnn_forward_class, and leave the same in-place prune."""
+    from schemanet_b200 import native
+    from schema_inference.graph import GNN
+    M = 1200                                         # >= Vc: class ingredients are distinct codes
+    sch = ho.synth_schema(M, K, Vc, seed=21)
+    gnn = GNN(M, D, num_layers=2).cuda()
+    gnn.load_state_dict(ho.synth_gnn(M, D, seed=22))
+    vw, ci = sch["vertex_weights"].cuda(), sch["class_ingredients"].cuda()
+    ew_a, ew_b, ew_c = (sch["edge_weights"].clone().cuda() for _ in range(3))
+    pack = gnn.param_pack()
+    cv1, ce1, f1 = native.class_side(pack, vw, ew_a, ci, thr, True, rsl, want_edges=True)
+    cv2, ce2, f2 = native.class_side(pack, vw, ew_b, ci, thr, True, rsl, want_edges=False)
+    cv3, ce3 = native.class_atlas(vw, ew_c, thr, True, rsl)
+    f3 = native.gnn_forward_class(pack, cv3, ce3, ci, thr)
+    assert ce2 is None
+    assert torch.equal(cv1, cv3) and torch.equal(cv2, cv3) and torch.equal(ce1, ce3)
+    assert torch.equal(ew_a, ew_c) and torch.equal(ew_b, ew_c)          # in-place prune of the parameter
+    assert torch.equal(f1, f3) and torch.equal(f2, f3)
+    # and against the oracle
+    atlas = ho.class_atlas(sch["vertex_weights"], sch["edge_weights"].clone(), sch["class_ingredients"], thr, rsl)
+    ref = ho.gnn_forward(ho.synth_gnn(M, D, seed=22), atlas["class_vertices"], atlas["class_edges"], sch["class_ingredients"], None)
+    rel_close(f2, ref, what="class embeddings (fused class side)")
+
+
 @pytest.mark.parametrize("K,Vc,masked,D", [(3, 300, False, 256), (5, 1024, False, 256), (9, 196, True, 256), (2, 33, True, 256),
                                           (3, 300, True, 512), (2, 500, False, 1024)])
 def test_gnn_tensor_core_path_vs_oracle(K, Vc, masked, D):

@@ -1,3 +1,2 @@
-for w in 12; do for sp in 1 2; do SCHEMANET_GRAPH_WARPS=$w SCHEMANET_GRAPH_SPLIT=$sp timeout 60 python tools/graph_bench.py 256 1024; done; done
-for w in 12; do SCHEMANET_GRAPH_WARPS=$w timeout 60 python tools/graph_bench.py 1024 8000; SCHEMANET_GRAPH_WARPS=$w timeout 60 python tools/graph_bench.py 64 128; SCHEMANET_GRAPH_WARPS=$w timeout 60 python tools/graph_bench.py 512 1024; done
-SCHEMANET_GRAPH_WARPS=8 timeout 60 python tools/graph_bench.py 512 1024
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for c in 0 48; do SCHEMANET_ADJ_CTAS=$c timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_g$c.json 2>gpurun_out/bench.err; done
