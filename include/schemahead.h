@@ -181,7 +181,11 @@ int sh_dev_gnn_forward(const sh_gnn_params *params, int G, int n_fixed, const in
 /* Stage 3a + class side of stage 3b in one call (what SchemaNetPredictor.forward does with get_atlas() followed by the
  * second self.gnn(...) of Matcher.forward, schema_net.py:177-184 + match.py:66-70): writes class_vertices [K,Vc],
  * class_edges [K,Vc,Vc] and the class embeddings feat_class [K,D].  The tensor-core path compacts every class graph to
- * its un-pruned vertices first (pruned vertices have all-zero edge rows/columns, so the result is unchanged). */
+ * its un-pruned vertices first (pruned vertices have all-zero edge rows/columns, so the result is unchanged).
+ * class_edges may be NULL on the tensor-core path (embed_dim % 256 == 0, embed_dim <= 1024, Vc >= 32): the normalised
+ * [K,Vc,Vc] tensor is then not materialised at all -- the adjacency operand is gathered from the (pruned) parameter and
+ * per-row normalisers -- which saves its 4*K*Vc*Vc bytes of HBM writes; feat_class is bit-identical either way.  The
+ * in-place prune of edge_weights (schema_net.py:164) happens in both cases. */
 size_t sh_class_side_workspace_bytes(int K, int Vc, int D);
 /* GNN.forward on the class graphs get_atlas() produced (match.py:66-70), given the prune threshold they were built with
  * (< 0: none): same result as sh_dev_gnn_forward, pruned vertices are skipped.  Workspace: sh_class_side_workspace_bytes. */

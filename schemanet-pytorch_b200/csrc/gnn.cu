@@ -261,47 +261,47 @@ pool_fc_kernel(const float *__restrict__ partial, int chunks, int D, int n_fixed
     }
 }
 
-// out[r, o] = sum_k A[r, k] W[o, k] for a tall-skinny A (the (M+1)-row embedding table).  (The generic tiled GEMM
-// launches only ~18 CTAs for this shape and took 0.11 ms.)
-// kRows rows per CTA; a lane keeps its slice of the kRows x D input rows in registers (D <= 256: 8 columns per lane), so
-// the inner loop is 8 coalesced loads of a W row + kRows*8 FMAs + kRows shuffle reductions per output feature.
+// out[r, o] = sum_k A[r, k] W[o, k] for a tall-skinny A (the (M+1)-row embedding / activation tables), D <= 256, D % 4 == 0.
+// (The generic tiled GEMM launches only ~18 CTAs for this shape and took 0.11 ms; a warp-per-output version with shuffle
+// reductions was latency-bound at 0.028 ms.)  kRows rows per CTA staged in shared memory; thread o owns output feature o
+// for all kRows rows: it streams its own row of W (16-byte loads, every fetched line is fully used over 8 steps and stays
+// in L1) against broadcast reads of the staged rows -- kRows independent FMA chains per thread, no reductions.
 template <int kRows>
 __global__ void __launch_bounds__(256)
 rows_linear_kernel(const float *__restrict__ A, const float *__restrict__ W, int rows, int D, float *__restrict__ out)
 {
-    const int r0 = blockIdx.x * kRows, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float a[kRows][8];
-#pragma unroll
+    __shared__ __align__(16) float As[kRows][256];
+    const int r0 = blockIdx.x * kRows, o = threadIdx.x;
     for (int i = 0; i < kRows; ++i)
+        if (o < D) As[i][o] = (r0 + i < rows) ? __ldg(A + (size_t)(r0 + i) * D + o) : 0.0f;
+    __syncthreads();
+    if (o >= D) return;
+    float acc[kRows];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int k = u * kWarp + lane;
-            a[i][u] = (r0 + i < rows && k < D) ? __ldg(A + (size_t)(r0 + i) * D + k) : 0.0f;
-        }
-    for (int o = warp; o < D; o += 8) {
-        const float *w = W + (size_t)o * D;
-        float wk[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int k = u * kWarp + lane;
-            wk[u] = k < D ? __ldg(w + k) : 0.0f;
-        }
+    for (int i = 0; i < kRows; ++i) acc[i] = 0.0f;
+    const float4 *w = reinterpret_cast<const float4 *>(W + (size_t)o * D);
+#pragma unroll 4
+    for (int k4 = 0; k4 < D / 4; ++k4) {
+        const float4 wv = __ldg(w + k4);
 #pragma unroll
         for (int i = 0; i < kRows; ++i) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc = fmaf(a[i][u], wk[u], acc);
-            acc = warp_sum(acc);
-            if (lane == 0 && r0 + i < rows) out[(size_t)(r0 + i) * D + o] = acc;
+            const float4 av = *reinterpret_cast<const float4 *>(&As[i][4 * k4]);
+            acc[i] = fmaf(av.x, wv.x, acc[i]);
+            acc[i] = fmaf(av.y, wv.y, acc[i]);
+            acc[i] = fmaf(av.z, wv.z, acc[i]);
+            acc[i] = fmaf(av.w, wv.w, acc[i]);
         }
     }
+#pragma unroll
+    for (int i = 0; i < kRows; ++i)
+        if (r0 + i < rows) out[(size_t)(r0 + i) * D + o] = acc[i];
 }
 
 int launch_rows_linear(const float *A, const float *W, int rows, int D, float *out, cudaStream_t st)
 {
-    SH_REQUIRE(D <= 256, "rows_linear: D <= 256 expected");
+    SH_REQUIRE(D <= 256 && D % 4 == 0, "rows_linear: D <= 256, D %% 4 == 0 expected");
     SH_LAUNCH("gnn_embed_table_linear", st,
-              rows_linear_kernel<4><<<ceil_div(rows, 4), 256, 0, st>>>(A, W, rows, D, out));
+              rows_linear_kernel<8><<<ceil_div(rows, 8), 256, 0, st>>>(A, W, rows, D, out));
     SH_CHECK_LAUNCH();
     return 0;
 }

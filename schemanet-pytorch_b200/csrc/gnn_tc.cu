@@ -47,6 +47,8 @@ struct GemmTcArgs {
     int identity_tail;        // adj GEMM: rows >= n_g carry an identity diagonal (class graphs compacted to their
                               // un-pruned vertices): such row blocks only visit their own diagonal k-blocks
     int batched_b;            // 1: B operand indexed by the graph, 0: shared (weights)
+    int skip_masked;          // 1: work units whose rows are all >= their graph's size are skipped in every epilogue
+                              // (nothing downstream reads those rows: class graphs reduced to their un-pruned vertices)
     // epilogue
     float *out_hi, *out_lo;      // EPI_STORE_SPLIT: Y hi/lo [G, n_fixed, 256]; EPI_LN_RELU_T_SPLIT: H^T hi/lo [G, 256, ldk]
     float *out_rows;             // EPI_LN_RELU_ROWS: H [G*n_fixed, 256]
@@ -158,7 +160,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
         const int mb = ub * CTAS + rank;   /* this CTA's 128-row block */                                 \
         const int n_g = (a.k_sizes && a.G > 1) ? a.k_sizes[g] : a.K_total;                                \
         /* units past the graph are skipped, except when the epilogue must still write their (zero) rows */ \
-        if (EPI == EPI_STORE_SPLIT && a.G > 1 && !a.identity_tail && ub * UB >= n_g) continue;            \
+        if ((EPI == EPI_STORE_SPLIT || a.skip_masked) && a.G > 1 && !a.identity_tail && ub * UB >= n_g) continue; \
+        if (a.skip_masked && a.G == 1 && a.row_sizes) {   /* flattened rows: unit inside one graph, past its size */ \
+            const int r0_ = ub * UB, gi_ = r0_ / a.rows_per_graph;                                        \
+            if ((r0_ + UB - 1) / a.rows_per_graph == gi_ && r0_ - gi_ * a.rows_per_graph >= a.row_sizes[gi_]) continue; \
+        }                                                                                                 \
         /* k-blocks [0, kA) cover the active range; with identity_tail a unit that holds rows >= n_g       \
            additionally visits the k-blocks of its own diagonal that are not in [0, kA) */                 \
         const int kA = (a.G > 1 && a.identity_tail && ub * UB >= n_g) ? 0 : max(1, ceil_div(n_g, G_BK));   \
@@ -398,6 +404,7 @@ embed_gather_t_kernel(const float *__restrict__ emb, const int64_t *__restrict__
     const int g = blockIdx.z;
     const int n_g = sizes ? sizes[g] : n_fixed;
     const int i0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    if (i0 >= max(32, (n_g + 31) / 32 * 32)) return;   // past the k-blocks the adjacency GEMM reads for this graph
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int r = ty; r < 32; r += 8) {       // node i0 + r, features d0 + tx (coalesced along d)
         const int i = i0 + r;
@@ -422,10 +429,12 @@ __global__ void __launch_bounds__(256) split_kernel(const float *__restrict__ x,
         split_tf32(x[i], hi[i], lo[i]);
 }
 
+constexpr int kTableSlices = 8;   // CTAs per class summing the pruned vertices' table rows (pool_table_rows_kernel)
+
 // pooled partials: partial[g, chunk, d] = sum over the chunk's nodes of H[g, i, d] * w[g, i]   (gnn.py:94-95)
 __global__ void __launch_bounds__(256)
 pool_rows_kernel(const float *__restrict__ H, const float *__restrict__ vertex_w, int ld_v, const int32_t *__restrict__ sizes,
-                 int n_fixed, int D, int chunks, float *__restrict__ partial)
+                 int n_fixed, int D, int chunks, float *__restrict__ partial, const float *__restrict__ extra)
 {
     const int g = blockIdx.y, chunk = blockIdx.x;
     const int n_g = sizes ? sizes[g] : n_fixed;
@@ -434,8 +443,55 @@ pool_rows_kernel(const float *__restrict__ H, const float *__restrict__ vertex_w
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float acc = 0.0f;
         for (int r = r0; r < r1; ++r) acc = fmaf(H[((size_t)g * n_fixed + r) * D + d], vertex_w[(size_t)g * ld_v + r], acc);
+        if (extra && chunk == 0) {                                 // vertices handled outside the GEMMs (class side)
+            float e = 0.0f;
+            for (int y = 0; y < kTableSlices; ++y) e += extra[((size_t)g * kTableSlices + y) * D + d];
+            acc += e;
+        }
         partial[((size_t)g * chunks + chunk) * D + d] = acc;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// class side: pruned vertices without GEMM rows
+// ---------------------------------------------------------------------------------------------------------------
+// A pruned class vertex has an all-zero row and column in class_edges, so in every layer ((E + E^T) / 2 + I) X keeps just
+// its own feature: its activations depend on its CODE only,
+//     T_0[c] = relu(LN(Emb[c] W_0^T + b_0)),   T_l[c] = relu(LN(T_{l-1}[c] W_l^T + b_l)),
+// (M + 1)-row tables that cost two tiny GEMMs, instead of ~55 % of the rows of every class-side GEMM.  The weighted
+// pooling of those vertices is a gather from the last table.
+// out[r, :] = relu(LN(Z[r, :] + bias)) -- one warp per row
+__global__ void __launch_bounds__(256)
+table_ln_relu_kernel(const float *__restrict__ Z, const float *__restrict__ bias, const float *__restrict__ gamma,
+                     const float *__restrict__ beta, float eps, int rows, int D, float *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const float *z = Z + (size_t)r * D;
+    float s = 0.0f;
+    for (int d = lane; d < D; d += kWarp) s += z[d] + bias[d];
+    const float mean = warp_sum(s) / (float)D;
+    float v = 0.0f;
+    for (int d = lane; d < D; d += kWarp) { const float t = z[d] + bias[d] - mean; v += t * t; }
+    const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)D + eps);
+    for (int d = lane; d < D; d += kWarp) out[(size_t)r * D + d] = fmaxf((z[d] + bias[d] - mean) * rstd * gamma[d] + beta[d], 0.0f);
+}
+
+// extra[k, y, d] = sum over the pruned vertices i >= n_act[k], i = n_act[k] + y (mod kTableSlices) (permuted order) of
+// w[k, i] * T[ids[k, i], d]; grid (K, kTableSlices), one thread per feature (D <= 256)
+__global__ void __launch_bounds__(256)
+pool_table_rows_kernel(const float *__restrict__ T, const int64_t *__restrict__ ids, const float *__restrict__ w,
+                       const int32_t *__restrict__ n_act, int Vc, int D, float *__restrict__ extra)
+{
+    const int k = blockIdx.x, d = threadIdx.x;
+    if (d >= D) return;
+    const int64_t *idk = ids + (size_t)k * Vc;
+    const float *wk = w + (size_t)k * Vc;
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int i = n_act[k] + blockIdx.y; i < Vc; i += kTableSlices) acc = fmaf(__ldg(T + (size_t)idk[i] * D + d), wk[i], acc);
+    extra[((size_t)k * kTableSlices + blockIdx.y) * D + d] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -508,8 +564,9 @@ class_perm_kernel(const float *__restrict__ cv, const int64_t *__restrict__ ci, 
 // Compacted class adjacency as hi/lo.  Only the parts the GEMM reads are written: the active corner (plus its padding
 // up to the tile edges) and the 128x128 diagonal blocks of row blocks that contain inactive vertices.
 __global__ void __launch_bounds__(256)
-class_adj_prep_kernel(const float *__restrict__ ce, int K, int Vc, int ldk, int unit_rows, const int32_t *__restrict__ n_act,
-                      const int32_t *__restrict__ old_of_new, float *__restrict__ adj_hi, float *__restrict__ adj_lo)
+class_adj_prep_kernel(const float *__restrict__ ce, int K, int Vc, int ldk, int unit_rows, int with_tail,
+                      const int32_t *__restrict__ n_act, const int32_t *__restrict__ old_of_new, float *__restrict__ adj_hi,
+                      float *__restrict__ adj_lo)
 {
     // One CTA per 32x32 tile; tiles outside the regions the GEMM reads exit at once.  (A persistent variant that walked
     // the tile space with two block barriers per tile measured 45 % slower.)
@@ -523,7 +580,7 @@ class_adj_prep_kernel(const float *__restrict__ ce, int K, int Vc, int ldk, int 
         const int rowsA = min(Vc, (nA + unit_rows - 1) / unit_rows * unit_rows), colsA = (nA + G_BK - 1) / G_BK * G_BK;
         const int ub = pi0 / unit_rows;
         const bool in_a = pi0 < rowsA && pj0 < colsA;
-        const bool in_b = (ub + 1) * unit_rows > nA && pj0 / unit_rows == ub;
+        const bool in_b = with_tail && (ub + 1) * unit_rows > nA && pj0 / unit_rows == ub;
         if (!in_a && !in_b) return;
         const float *cek = ce + (size_t)k * Vc * Vc;
         const int32_t *old = old_of_new + (size_t)k * Vc;
@@ -596,8 +653,9 @@ __device__ __forceinline__ void adj_fill_strip(float *__restrict__ adj_hi, float
 
 __global__ void __launch_bounds__(kAdjWarps * 32)
 class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ rowinv, int K, int Vc, int ldk, int unit_rows,
-                     int remove_self_loop, const int32_t *__restrict__ n_act, const int32_t *__restrict__ old_of_new,
-                     float *__restrict__ adj_hi, float *__restrict__ adj_lo, int ctas_per_class)
+                     int with_tail, int remove_self_loop, const int32_t *__restrict__ n_act,
+                     const int32_t *__restrict__ old_of_new, float *__restrict__ adj_hi, float *__restrict__ adj_lo,
+                     int ctas_per_class)
 {
     __shared__ float tiles[kAdjWarps][2][32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -623,7 +681,7 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
             const int a_end = pi0 < rowsA ? colsA : 0;                  // region A: the active corner up to the tile edges
             if (a_end > act_end) adj_fill_strip(adj_hi, adj_lo, base, ldk, Vc, pi0, act_end, a_end, lane);
             const int ub = pi0 / unit_rows;                             // region B: diagonal blocks with inactive vertices
-            if ((ub + 1) * unit_rows > nA) {
+            if (with_tail && (ub + 1) * unit_rows > nA) {
                 const int b0 = max(ub * unit_rows, max(act_end, a_end)), b1 = (ub + 1) * unit_rows;
                 if (b1 > b0) adj_fill_strip(adj_hi, adj_lo, base, ldk, Vc, pi0, b0, b1, lane);
             }
@@ -766,7 +824,7 @@ bool gnn_tc_supported(int D, int n_fixed)
 struct TcBuffers {
     float *adj_hi, *adj_lo, *xt_hi, *xt_lo, *xt2_hi, *xt2_lo, *y_hi, *y_lo, *w_hi, *w_lo, *h_rows;
     int32_t *n_act, *old_of_new;
-    float *rowinv;
+    float *rowinv, *pool_extra;
     int64_t *pid;
     float *pvw;
     int ldk;
@@ -795,6 +853,7 @@ static TcBuffers carve_tc(void *base, int G, int n_fixed, int D)
     b.n_act = (int32_t *)(p + off); off += al256((size_t)G * 4);
     b.old_of_new = (int32_t *)(p + off); off += al256((size_t)G * n_fixed * 4);
     b.rowinv = (float *)(p + off); off += al256((size_t)G * n_fixed * 4);
+    b.pool_extra = (float *)(p + off); off += al256((size_t)G * kTableSlices * D * 4);
     b.pid = (int64_t *)(p + off); off += al256((size_t)G * n_fixed * 8);
     b.pvw = (float *)(p + off); off += al256((size_t)G * n_fixed * 4);
     b.bytes = off;
@@ -875,20 +934,44 @@ static int tmap3(CUtensorMap *m, const float *p, uint64_t cols, uint64_t rows, u
 
 // All GNN layers given a prepared hi/lo adjacency in b.adj_*.  k_sizes: active size per graph for the adjacency GEMM
 // (null = n_fixed); identity_tail: see GemmTcArgs; row_sizes: real rows per graph for masking (null = all).
+static bool layer0_fused(const sh_gnn_params *p, int G, int n_fixed)
+{
+    return p->embed_dim == G_BN && (int64_t)(p->num_codes + 1) <= (int64_t)G * n_fixed;
+}
+
+// table_tail (class side, needs layer0_fused): rows >= row_sizes[g] are pruned vertices; they get no GEMM rows, their
+// pooled contribution comes from the per-code activation tables (see table_ln_relu_kernel).
 static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *k_sizes, int identity_tail,
                          const int32_t *row_sizes, const int64_t *ids, int ld_ids, const float *vertex_w, int ld_v,
-                         const TcBuffers &b, int chunks, float *partial, cudaStream_t st)
+                         const TcBuffers &b, int chunks, float *partial, cudaStream_t st, bool table_tail = false)
 {
     const int D = p->embed_dim, ldk = b.ldk;
     // Layer-0 shortcut (embed_dim 256): (Adj X0) W0^T = Adj (X0 W0^T) and X0 = Emb[ids], so the first Linear is applied to
     // the (M+1)-row embedding TABLE once (a tiny fp32 GEMM) instead of to every node of every graph; layer 0 then is a
     // single adjacency GEMM with bias + LayerNorm + ReLU fused in its epilogue.  The table product is staged in the
     // (still unused) Y_lo buffer, which it fits whenever the batch has at least M+1 node slots.
-    const bool fuse0 = D == G_BN && (int64_t)(p->num_codes + 1) <= (int64_t)G * n_fixed;
+    const bool fuse0 = layer0_fused(p, G, n_fixed);
+    SH_REQUIRE(!table_tail || (fuse0 && row_sizes && !identity_tail), "run_layers_tc: table tail needs the fused layer 0");
     const float *table = p->embedding;
     if (fuse0) {
         if (launch_rows_linear(p->embedding, p->lin_w[0], p->num_codes + 1, D, b.y_lo, st)) return 1;
         table = b.y_lo;
+    }
+    if (table_tail) {
+        // T_l in h_rows, the next layer's product in y_hi: both are free until the GEMMs below reach them, and the
+        // pooled sums of the pruned vertices are taken (into pool_extra) before that
+        const int rows = p->num_codes + 1;
+        for (int l = 0; l < p->num_layers; ++l) {
+            const float *z = b.y_lo;
+            if (l > 0) {
+                if (launch_rows_linear(b.h_rows, p->lin_w[l], rows, D, b.y_hi, st)) return 1;
+                z = b.y_hi;
+            }
+            SH_LAUNCH("gnn_table_ln_relu", st, table_ln_relu_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(z, p->lin_b[l], p->ln_w[l], p->ln_b[l], p->ln_eps, rows, D, b.h_rows));
+            SH_CHECK_LAUNCH();
+        }
+        SH_LAUNCH("gnn_pool_table_rows", st, pool_table_rows_kernel<<<dim3(G, kTableSlices), 256, 0, st>>>(b.h_rows, ids, vertex_w, row_sizes, n_fixed, D, b.pool_extra));
+        SH_CHECK_LAUNCH();
     }
     {
         dim3 grid2(ceil_div(ldk, 32), D / 32, G);
@@ -919,7 +1002,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
         CUtensorMap m1p[4] = {adjm[0], adjm[1], xtm2[0], xtm2[1]};
         GemmTcArgs a{};
         a.G = G; a.rows_per_graph = n_fixed; a.M_total = n_fixed; a.K_total = n_fixed; a.N_total = D;
-        a.k_sizes = k_sizes; a.identity_tail = identity_tail; a.batched_b = 1;
+        a.k_sizes = k_sizes; a.identity_tail = identity_tail; a.batched_b = 1; a.skip_masked = table_tail ? 1 : 0;
         if (l == 0 && fuse0) {
             // H1 = relu(LN(Adj (X0 W0^T) + b0)) in one kernel
             a.row_sizes = row_sizes;
@@ -940,6 +1023,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
         // H = relu(LN(Y W^T + b))
         GemmTcArgs c{};
         c.G = 1; c.rows_per_graph = n_fixed; c.M_total = G * n_fixed; c.K_total = D; c.N_total = D; c.row_sizes = row_sizes; c.batched_b = 0;
+        c.skip_masked = table_tail ? 1 : 0;
         c.bias = p->lin_b[l]; c.gamma = p->ln_w[l]; c.beta = p->ln_b[l]; c.eps = p->ln_eps;
         c.out_hi = xin_hi; c.out_lo = xin_lo; c.ldk = ldk; c.out_rows = b.h_rows;
         CUtensorMap m2[4] = {ym[0], ym[1], wm[0], wm[1]};
@@ -968,7 +1052,8 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
         }
     }
     dim3 grid(chunks, G);
-    SH_LAUNCH("gnn_pool_rows", st, pool_rows_kernel<<<grid, 256, 0, st>>>(b.h_rows, vertex_w, ld_v, row_sizes, n_fixed, D, chunks, partial));
+    SH_LAUNCH("gnn_pool_rows", st, pool_rows_kernel<<<grid, 256, 0, st>>>(b.h_rows, vertex_w, ld_v, row_sizes, n_fixed, D, chunks, partial,
+                                                                          table_tail ? b.pool_extra : nullptr));
     SH_CHECK_LAUNCH();
     return 0;
 }
@@ -984,7 +1069,19 @@ int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *si
     return run_layers_tc(p, G, n_fixed, sizes, 0, sizes, ids, ld_v, vertex_w, ld_v, b, chunks, partial, st);
 }
 
-// Class side with the graphs compacted to their un-pruned vertices (see class_perm_kernel).
+// The class graphs' layers after the adjacency operand is in place.  embed_dim 256: pruned vertices are served from the
+// per-code activation tables and the GEMMs only see the un-pruned ones; wider embeddings keep every vertex in the GEMMs
+// and let the row blocks of pruned vertices visit just their identity diagonal.
+static bool class_table_tail(const sh_gnn_params *p, int K, int Vc) { return layer0_fused(p, K, Vc); }
+
+static int class_layers_tc(const sh_gnn_params *p, int K, int Vc, const TcBuffers &b, int chunks, float *partial, cudaStream_t st)
+{
+    if (class_table_tail(p, K, Vc))
+        return run_layers_tc(p, K, Vc, b.n_act, 0, b.n_act, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st, true);
+    return run_layers_tc(p, K, Vc, b.n_act, 1, nullptr, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st);
+}
+
+// Class side with the graphs compacted to their un-pruned vertices (see class_perm_kernel), from a materialised atlas.
 int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *class_vertices, const float *class_edges,
                          const int64_t *class_ingredients, float prune_threshold, int chunks, float *partial,
                          void *workspace, cudaStream_t st)
@@ -998,9 +1095,10 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
     SH_CHECK_LAUNCH();
     SH_LAUNCH("class_adj_prep_kernel", st,
               class_adj_prep_kernel<<<dim3(ceil_div(b.ldk, 32), ceil_div(Vc, 32), K), 256, 0, st>>>(
-                  class_edges, K, Vc, b.ldk, G_BM * gemm_ctas(), b.n_act, b.old_of_new, b.adj_hi, b.adj_lo));
+                  class_edges, K, Vc, b.ldk, G_BM * gemm_ctas(), class_table_tail(p, K, Vc) ? 0 : 1, b.n_act, b.old_of_new,
+                  b.adj_hi, b.adj_lo));
     SH_CHECK_LAUNCH();
-    return run_layers_tc(p, K, Vc, b.n_act, 1, nullptr, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st);
+    return class_layers_tc(p, K, Vc, b, chunks, partial, st);
 }
 
 // Stage 3a + class side fused (sh_dev_class_side on the tensor-core path): the atlas pass leaves the per-row normalisers,
@@ -1029,11 +1127,11 @@ int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc
         if (forced > 0) cpc = forced;
         SH_LAUNCH("class_adj_prep_kernel", st,
                   class_adj_raw_kernel<<<K * cpc, kAdjWarps * 32, 0, st>>>(edge_weights, b.rowinv, K, Vc, b.ldk, G_BM * gemm_ctas(),
-                                                                           remove_self_loop, b.n_act, b.old_of_new, b.adj_hi,
-                                                                           b.adj_lo, cpc));
+                                                                           class_table_tail(p, K, Vc) ? 0 : 1, remove_self_loop,
+                                                                           b.n_act, b.old_of_new, b.adj_hi, b.adj_lo, cpc));
         SH_CHECK_LAUNCH();
     }
-    return run_layers_tc(p, K, Vc, b.n_act, 1, nullptr, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st);
+    return class_layers_tc(p, K, Vc, b, chunks, partial, st);
 }
 
 }  // namespace sh
