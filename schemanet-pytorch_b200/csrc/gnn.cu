@@ -261,47 +261,111 @@ pool_fc_kernel(const float *__restrict__ partial, int chunks, int D, int n_fixed
     }
 }
 
-// out[r, o] = sum_k A[r, k] W[o, k] for a tall-skinny A (the (M+1)-row embedding / activation tables), D <= 256, D % 4 == 0.
+// out[r, o] = sum_k A[r, k] W[o, k] for a tall-skinny A (the (M+1)-row embedding / activation tables), D <= 256, D % 32 == 0;
+// optionally also act[r, :] = relu(LayerNorm(out[r, :] + bias)) (one layer of the per-code activation tables, gnn_tc.cu).
 // (The generic tiled GEMM launches only ~18 CTAs for this shape and took 0.11 ms; a warp-per-output version with shuffle
-// reductions was latency-bound at 0.028 ms.)  kRows rows per CTA staged in shared memory; thread o owns output feature o
-// for all kRows rows: it streams its own row of W (16-byte loads, every fetched line is fully used over 8 steps and stays
-// in L1) against broadcast reads of the staged rows -- kRows independent FMA chains per thread, no reductions.
+// reductions 0.028 ms; thread-per-output streaming its own W row 0.018 ms, L1-tag bound on 32 lines per request.)
+// kRows rows per CTA staged in shared memory; W goes through shared memory in 32-column slabs, read with coalesced 128 B
+// row segments and stored transposed (stride 257: conflict-free both ways); thread o owns output feature o for all kRows
+// rows -- kRows independent FMA chains per thread, no reductions.
 template <int kRows>
 __global__ void __launch_bounds__(256)
-rows_linear_kernel(const float *__restrict__ A, const float *__restrict__ W, int rows, int D, float *__restrict__ out)
+rows_linear_kernel(const float *__restrict__ A, const float *__restrict__ W, int rows, int D, float *__restrict__ out,
+                   const float *__restrict__ bias, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
+                   float *__restrict__ act)
 {
     __shared__ __align__(16) float As[kRows][256];
-    const int r0 = blockIdx.x * kRows, o = threadIdx.x;
-    for (int i = 0; i < kRows; ++i)
-        if (o < D) As[i][o] = (r0 + i < rows) ? __ldg(A + (size_t)(r0 + i) * D + o) : 0.0f;
-    __syncthreads();
-    if (o >= D) return;
+    __shared__ float Ws[32][257];
+    __shared__ float red[8][kRows];
+    const int r0 = blockIdx.x * kRows, o = threadIdx.x, lane = o & 31, warp = o >> 5;
+    for (int i = 0; i < kRows; ++i) As[i][o] = (o < D && r0 + i < rows) ? __ldg(A + (size_t)(r0 + i) * D + o) : 0.0f;
     float acc[kRows];
 #pragma unroll
     for (int i = 0; i < kRows; ++i) acc[i] = 0.0f;
-    const float4 *w = reinterpret_cast<const float4 *>(W + (size_t)o * D);
-#pragma unroll 4
-    for (int k4 = 0; k4 < D / 4; ++k4) {
-        const float4 wv = __ldg(w + k4);
+    // W slabs are software-pipelined: the next slab's 8 float4 per thread are in flight while the current one is used
+    float4 wn[8];
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < kRows; ++i) {
-            const float4 av = *reinterpret_cast<const float4 *>(&As[i][4 * k4]);
-            acc[i] = fmaf(av.x, wv.x, acc[i]);
-            acc[i] = fmaf(av.y, wv.y, acc[i]);
-            acc[i] = fmaf(av.z, wv.z, acc[i]);
-            acc[i] = fmaf(av.w, wv.w, acc[i]);
+        for (int j = 0; j < 8; ++j) {         // rows j*32 + o/8 of W, float4 (o % 8) of the slab
+            const int row = j * 32 + (o >> 3);
+            wn[j] = row < D ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)row * D + k0 + (o & 7) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < D; k0 += 32) {
+        __syncthreads();                      // previous slab consumed (first pass: As visible)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int row = j * 32 + (o >> 3), c4 = (o & 7) * 4;
+            Ws[c4 + 0][row] = wn[j].x; Ws[c4 + 1][row] = wn[j].y; Ws[c4 + 2][row] = wn[j].z; Ws[c4 + 3][row] = wn[j].w;
+        }
+        if (k0 + 32 < D) fetch(k0 + 32);
+        __syncthreads();
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+            const float w0 = Ws[4 * k4][o], w1 = Ws[4 * k4 + 1][o], w2 = Ws[4 * k4 + 2][o], w3 = Ws[4 * k4 + 3][o];
+#pragma unroll
+            for (int i = 0; i < kRows; ++i) {
+                const float4 av = *reinterpret_cast<const float4 *>(&As[i][k0 + 4 * k4]);
+                acc[i] = fmaf(av.x, w0, acc[i]);
+                acc[i] = fmaf(av.y, w1, acc[i]);
+                acc[i] = fmaf(av.z, w2, acc[i]);
+                acc[i] = fmaf(av.w, w3, acc[i]);
+            }
         }
     }
+    const bool live = o < D;
+    if (out && live) {
 #pragma unroll
-    for (int i = 0; i < kRows; ++i)
-        if (r0 + i < rows) out[(size_t)(r0 + i) * D + o] = acc[i];
+        for (int i = 0; i < kRows; ++i)
+            if (r0 + i < rows) out[(size_t)(r0 + i) * D + o] = acc[i];
+    }
+    if (act == nullptr) return;
+    // LayerNorm over the D features of each row (two-pass: mean, then centred variance), block reductions via `red`
+    const float bo = live ? bias[o] : 0.0f;
+    float mean[kRows], rstd[kRows];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+        acc[i] = live ? acc[i] + bo : 0.0f;
+        const float s = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; ++w) s += red[w][i];
+        mean[i] = s / (float)D;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+        const float t = live ? acc[i] - mean[i] : 0.0f;
+        const float s = warp_sum(t * t);
+        if (lane == 0) red[warp][i] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; ++w) s += red[w][i];
+        rstd[i] = 1.0f / sqrtf(s / (float)D + eps);
+    }
+    if (live) {
+        const float g = gamma[o], be = beta[o];
+#pragma unroll
+        for (int i = 0; i < kRows; ++i)
+            if (r0 + i < rows) act[(size_t)(r0 + i) * D + o] = fmaxf((acc[i] - mean[i]) * rstd[i] * g + be, 0.0f);
+    }
 }
 
-int launch_rows_linear(const float *A, const float *W, int rows, int D, float *out, cudaStream_t st)
+int launch_rows_linear(const float *A, const float *W, int rows, int D, float *out, cudaStream_t st, const float *bias,
+                       const float *gamma, const float *beta, float eps, float *act)
 {
-    SH_REQUIRE(D <= 256 && D % 4 == 0, "rows_linear: D <= 256, D %% 4 == 0 expected");
+    SH_REQUIRE(D <= 256 && D % 32 == 0, "rows_linear: D <= 256, D %% 32 == 0 expected");
+    SH_REQUIRE(out || act, "rows_linear: no output");
     SH_LAUNCH("gnn_embed_table_linear", st,
-              rows_linear_kernel<8><<<ceil_div(rows, 8), 256, 0, st>>>(A, W, rows, D, out));
+              rows_linear_kernel<8><<<ceil_div(rows, 8), 256, 0, st>>>(A, W, rows, D, out, bias, gamma, beta, eps, act));
     SH_CHECK_LAUNCH();
     return 0;
 }

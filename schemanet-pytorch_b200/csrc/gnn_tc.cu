@@ -394,32 +394,37 @@ adj_prep_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const in
     }
 }
 
-// X0^T[g, d, i] = Emb[ids[g, i], d] as hi/lo (gnn.py:91), zero for i >= n_g.  32x32 tile transpose.
+// X0^T[g, d, i] = Emb[ids[g, i], d] as hi/lo (gnn.py:91), zero for i >= n_g.  One CTA per (32 nodes, 256 features, graph):
+// each warp reads whole 1 KB table rows (8 coalesced loads per node, the id fetched once), the slab is transposed through
+// shared memory and written as 128-byte row segments of X^T.
 __global__ void __launch_bounds__(256)
 embed_gather_t_kernel(const float *__restrict__ emb, const int64_t *__restrict__ ids, int ld_ids,
                       const int32_t *__restrict__ sizes, int n_fixed, int ldk, int D, float *__restrict__ xt_hi,
                       float *__restrict__ xt_lo)
 {
-    __shared__ float tile[32][33];
+    __shared__ float tile[32][257];
     const int g = blockIdx.z;
     const int n_g = sizes ? sizes[g] : n_fixed;
-    const int i0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int i0 = blockIdx.x * 32, d0 = blockIdx.y * 256;
     if (i0 >= max(32, (n_g + 31) / 32 * 32)) return;   // past the k-blocks the adjacency GEMM reads for this graph
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < 32; r += 8) {       // node i0 + r, features d0 + tx (coalesced along d)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dn = min(256, D - d0);                    // features of this slab (multiple of 32)
+    for (int r = warp; r < 32; r += 8) {               // node i0 + r
         const int i = i0 + r;
-        tile[r][tx] = (i < n_g) ? emb[(size_t)ids[(size_t)g * ld_ids + i] * D + d0 + tx] : 0.0f;
+        const float *row = (i < n_g) ? emb + (size_t)ids[(size_t)g * ld_ids + i] * D + d0 : nullptr;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c * 32 < dn) tile[r][c * 32 + lane] = row ? __ldg(row + c * 32 + lane) : 0.0f;
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {       // feature d0 + r, nodes i0 + tx (coalesced along i)
-        const int d = d0 + r, i = i0 + tx;
-        if (i < ldk) {
-            float h, l;
-            split_tf32(tile[tx][r], h, l);
-            const size_t o = ((size_t)g * D + d) * ldk + i;
-            xt_hi[o] = h;
-            xt_lo[o] = l;
-        }
+    const int i = i0 + lane;
+    if (i >= ldk) return;
+    for (int d = warp; d < dn; d += 8) {               // feature d0 + d, nodes i0 .. i0 + 31 (coalesced along i)
+        float h, l;
+        split_tf32(tile[lane][d], h, l);
+        const size_t o = ((size_t)g * D + d0 + d) * ldk + i;
+        xt_hi[o] = h;
+        xt_lo[o] = l;
     }
 }
 
@@ -459,25 +464,8 @@ pool_rows_kernel(const float *__restrict__ H, const float *__restrict__ vertex_w
 // its own feature: its activations depend on its CODE only,
 //     T_0[c] = relu(LN(Emb[c] W_0^T + b_0)),   T_l[c] = relu(LN(T_{l-1}[c] W_l^T + b_l)),
 // (M + 1)-row tables that cost two tiny GEMMs, instead of ~55 % of the rows of every class-side GEMM.  The weighted
-// pooling of those vertices is a gather from the last table.
-// out[r, :] = relu(LN(Z[r, :] + bias)) -- one warp per row
-__global__ void __launch_bounds__(256)
-table_ln_relu_kernel(const float *__restrict__ Z, const float *__restrict__ bias, const float *__restrict__ gamma,
-                     const float *__restrict__ beta, float eps, int rows, int D, float *__restrict__ out)
-{
-    const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= rows) return;
-    const float *z = Z + (size_t)r * D;
-    float s = 0.0f;
-    for (int d = lane; d < D; d += kWarp) s += z[d] + bias[d];
-    const float mean = warp_sum(s) / (float)D;
-    float v = 0.0f;
-    for (int d = lane; d < D; d += kWarp) { const float t = z[d] + bias[d] - mean; v += t * t; }
-    const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)D + eps);
-    for (int d = lane; d < D; d += kWarp) out[(size_t)r * D + d] = fmaxf((z[d] + bias[d] - mean) * rstd * gamma[d] + beta[d], 0.0f);
-}
-
+// pooling of those vertices is a gather from the last table.  (The tables come from rows_linear_kernel, gnn.cu, with
+// the bias + LayerNorm + ReLU fused.)
 // extra[k, y, d] = sum over the pruned vertices i >= n_act[k], i = n_act[k] + y (mod kTableSlices) (permuted order) of
 // w[k, i] * T[ids[k, i], d]; grid (K, kTableSlices), one thread per feature (D <= 256)
 __global__ void __launch_bounds__(256)
@@ -940,7 +928,7 @@ static bool layer0_fused(const sh_gnn_params *p, int G, int n_fixed)
 }
 
 // table_tail (class side, needs layer0_fused): rows >= row_sizes[g] are pruned vertices; they get no GEMM rows, their
-// pooled contribution comes from the per-code activation tables (see table_ln_relu_kernel).
+// pooled contribution comes from the per-code activation tables (see pool_table_rows_kernel).
 static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *k_sizes, int identity_tail,
                          const int32_t *row_sizes, const int64_t *ids, int ld_ids, const float *vertex_w, int ld_v,
                          const TcBuffers &b, int chunks, float *partial, cudaStream_t st, bool table_tail = false)
@@ -954,27 +942,27 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     SH_REQUIRE(!table_tail || (fuse0 && row_sizes && !identity_tail), "run_layers_tc: table tail needs the fused layer 0");
     const float *table = p->embedding;
     if (fuse0) {
-        if (launch_rows_linear(p->embedding, p->lin_w[0], p->num_codes + 1, D, b.y_lo, st)) return 1;
+        // with a table tail the same launch also emits T_0 = relu(LN(P_0 + b_0)) into h_rows (free until the last layer)
+        if (launch_rows_linear(p->embedding, p->lin_w[0], p->num_codes + 1, D, b.y_lo, st, p->lin_b[0], p->ln_w[0], p->ln_b[0],
+                               p->ln_eps, table_tail ? b.h_rows : nullptr))
+            return 1;
         table = b.y_lo;
     }
     if (table_tail) {
-        // T_l in h_rows, the next layer's product in y_hi: both are free until the GEMMs below reach them, and the
-        // pooled sums of the pruned vertices are taken (into pool_extra) before that
+        // T_l ping-pongs between h_rows and y_hi: both are free until the GEMMs below reach them, and the pooled sums of
+        // the pruned vertices are taken (into pool_extra) before that
         const int rows = p->num_codes + 1;
-        for (int l = 0; l < p->num_layers; ++l) {
-            const float *z = b.y_lo;
-            if (l > 0) {
-                if (launch_rows_linear(b.h_rows, p->lin_w[l], rows, D, b.y_hi, st)) return 1;
-                z = b.y_hi;
-            }
-            SH_LAUNCH("gnn_table_ln_relu", st, table_ln_relu_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(z, p->lin_b[l], p->ln_w[l], p->ln_b[l], p->ln_eps, rows, D, b.h_rows));
-            SH_CHECK_LAUNCH();
+        float *cur = b.h_rows, *nxt = b.y_hi;
+        for (int l = 1; l < p->num_layers; ++l) {
+            if (launch_rows_linear(cur, p->lin_w[l], rows, D, nullptr, st, p->lin_b[l], p->ln_w[l], p->ln_b[l], p->ln_eps, nxt))
+                return 1;
+            float *t = cur; cur = nxt; nxt = t;
         }
-        SH_LAUNCH("gnn_pool_table_rows", st, pool_table_rows_kernel<<<dim3(G, kTableSlices), 256, 0, st>>>(b.h_rows, ids, vertex_w, row_sizes, n_fixed, D, b.pool_extra));
+        SH_LAUNCH("gnn_pool_table_rows", st, pool_table_rows_kernel<<<dim3(G, kTableSlices), 256, 0, st>>>(cur, ids, vertex_w, row_sizes, n_fixed, D, b.pool_extra));
         SH_CHECK_LAUNCH();
     }
     {
-        dim3 grid2(ceil_div(ldk, 32), D / 32, G);
+        dim3 grid2(ceil_div(ldk, 32), ceil_div(D, 256), G);
         SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(table, ids, ld_ids, row_sizes, n_fixed, ldk, D, b.xt_hi, b.xt_lo));
         SH_CHECK_LAUNCH();
     }

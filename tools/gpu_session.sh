@@ -13,5 +13,5 @@ echo "rc=$?" >> gpurun_out/session.log
 echo "== ncu launch list" >> gpurun_out/session.log
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>> gpurun_out/session.log
 echo "== ncu full: graph build / discretize_tc / atlas" >> gpurun_out/session.log
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"gemm3x|discretize_tc|instance_graph|class_edges|class_adj_prep" -s 9 -c 9 -o gpurun_out/prof_head python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>> gpurun_out/session.log
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"gemm3x|discretize_tc|instance_graph|class_edges|class_adj_raw" -s 9 -c 9 -o gpurun_out/prof_head python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>> gpurun_out/session.log
 tail -60 gpurun_out/session.log
