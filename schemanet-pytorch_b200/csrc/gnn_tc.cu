@@ -394,6 +394,103 @@ adj_prep_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const in
     }
 }
 
+// Same result as adj_prep_kernel with the work organised like class_adj_raw_kernel below: (E + E^T) / 2 is symmetric,
+// so a WARP owns the tile pair (I, J) / (J, I), I <= J, reads both source tiles once (16 independent row loads per lane
+// in flight) and writes both results; the remaining items of a graph's work list are 32-row strips of zero padding.
+// ctas_per_graph CTAs of 4 warps walk each graph's list.  (One CTA per 32x32 tile was latency-bound: 0.045 ms for 118 MB.)
+__device__ __forceinline__ void adj_zero_strip(float *__restrict__ adj_hi, float *__restrict__ adj_lo, size_t base, int ldk,
+                                               int rows, int i0, int c0, int c1, int lane)
+{
+    const int nr = min(32, rows - i0);
+    for (int j = c0 + lane; j < c1; j += 32) {
+        float *ph = adj_hi + base + (size_t)i0 * ldk + j, *pl = adj_lo + base + (size_t)i0 * ldk + j;
+        for (int r = 0; r < nr; ++r) { *ph = 0.0f; *pl = 0.0f; ph += ldk; pl += ldk; }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+adj_sym_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int32_t *__restrict__ sizes, int n_fixed, int ldk,
+               float *__restrict__ adj_hi, float *__restrict__ adj_lo, int ctas_per_graph)
+{
+    __shared__ float tiles[4][2][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x / ctas_per_graph;
+    const int wid = (blockIdx.x % ctas_per_graph) * 4 + warp, nw = ctas_per_graph * 4;
+    const int n_g = sizes ? sizes[g] : n_fixed;
+    const int ld = e_ld > 0 ? e_ld : n_g;
+    const float *Eg = E + (size_t)g * e_batch;
+    const size_t base = (size_t)g * n_fixed * ldk;
+    const int nt = (n_g + 31) / 32, pairs = nt * (nt + 1) / 2, TR = (n_fixed + 31) / 32;
+    float (*T)[33] = tiles[warp][0];
+    float (*S)[33] = tiles[warp][1];
+    for (int item = wid; item < pairs + TR; item += nw) {
+        if (item >= pairs) {                 // zero padding right of (rows < n_g) / instead of (rows >= n_g) the corner
+            const int i0 = (item - pairs) * 32;
+            adj_zero_strip(adj_hi, adj_lo, base, ldk, n_fixed, i0, i0 < n_g ? nt * 32 : 0, ldk, lane);
+            continue;
+        }
+        int J = (int)((sqrtf(8.0f * (float)item + 1.0f) - 1.0f) * 0.5f);
+        while ((J + 1) * (J + 2) / 2 <= item) ++J;
+        while (J * (J + 1) / 2 > item) --J;
+        const int I = item - J * (J + 1) / 2;
+        const int i0 = I * 32, j0 = J * 32;
+        const bool vi = i0 + lane < n_g, vj = j0 + lane < n_g;
+        const int nvi = min(32, n_g - i0), nvj = min(32, n_g - j0);
+        // T[r][lane] = E[j0 + r][i0 + lane]
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (vi && rb + u < nvj) ? __ldg(Eg + (size_t)(j0 + rb + u) * ld + i0 + lane) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) T[rb + u][lane] = v[u];
+        }
+        __syncwarp();
+        const bool col_ok = j0 + lane < ldk;
+        float *ph = adj_hi + base + (size_t)i0 * ldk + j0 + lane, *pl = adj_lo + base + (size_t)i0 * ldk + j0 + lane;
+        const int diag = (I == J) ? lane : -1;
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (vj && rb + u < nvi) ? __ldg(Eg + (size_t)(i0 + rb + u) * ld + j0 + lane) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int r = rb + u;
+                // outside the n_g x n_g corner both terms are 0 and there is no identity (padded vertices: gnn.py:27-30 on
+                // zero-padded edges would add it, but those rows are masked and their columns multiply zero features)
+                float sym = 0.0f;
+                if (r < nvi && vj) sym = (v[u] + T[lane][r]) / 2.0f + ((r == diag) ? 1.0f : 0.0f);
+                S[r][lane] = sym;
+                if (col_ok && i0 + r < n_fixed) {
+                    float h, l;
+                    split_tf32(sym, h, l);
+                    *ph = h;
+                    *pl = l;
+                }
+                ph += ldk;
+                pl += ldk;
+            }
+        }
+        __syncwarp();
+        if (I != J && i0 + lane < ldk) {
+            ph = adj_hi + base + (size_t)j0 * ldk + i0 + lane;
+            pl = adj_lo + base + (size_t)j0 * ldk + i0 + lane;
+            const int rows = min(32, n_fixed - j0);
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) {
+                float h, l;
+                split_tf32(S[lane][r], h, l);
+                *ph = h;
+                *pl = l;
+                ph += ldk;
+                pl += ldk;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // X0^T[g, d, i] = Emb[ids[g, i], d] as hi/lo (gnn.py:91), zero for i >= n_g.  One CTA per (32 nodes, 256 features, graph):
 // each warp reads whole 1 KB table rows (8 coalesced loads per node, the id fetched once), the slab is transposed through
 // shared memory and written as 128-byte row segments of X^T.
@@ -1051,8 +1148,14 @@ int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *si
                    float *partial, void *workspace, cudaStream_t st)
 {
     TcBuffers b = carve_tc(workspace, G, n_fixed, p->embed_dim);
-    dim3 grid(ceil_div(b.ldk, 32), ceil_div(n_fixed, 32), G);
-    SH_LAUNCH("gnn_adj_prep", st, adj_prep_kernel<<<grid, 256, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj_hi, b.adj_lo));
+    if (getenv("SCHEMANET_ADJ_TILED") != nullptr) {
+        dim3 grid(ceil_div(b.ldk, 32), ceil_div(n_fixed, 32), G);
+        SH_LAUNCH("gnn_adj_prep", st, adj_prep_kernel<<<grid, 256, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj_hi, b.adj_lo));
+    } else {
+        const int tr = ceil_div(n_fixed, 32);
+        const int cpg = max(1, min(16, ceil_div(tr * (tr + 1) / 2 + tr, 4 * 4)));   // ~4 items per warp at full size
+        SH_LAUNCH("gnn_adj_prep", st, adj_sym_kernel<<<G * cpg, 128, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj_hi, b.adj_lo, cpg));
+    }
     SH_CHECK_LAUNCH();
     return run_layers_tc(p, G, n_fixed, sizes, 0, sizes, ids, ld_v, vertex_w, ld_v, b, chunks, partial, st);
 }
