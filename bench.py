@@ -27,7 +27,7 @@ import torch  # noqa: E402
 
 WORKLOAD = "cfg2"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r01_ncu_full_kernels.txt (ncu --set full, cfg2)
-NCU_TRAFFIC = {"adjacency_gemm": 692.2e6, "discretize": 39.6e6, "graph_build": 42.1e6, "atlas": 425.3e6}
+NCU_TRAFFIC = {"adjacency_gemm": 384.1e6, "discretize": 39.6e6, "graph_build": 41.8e6, "atlas": 423.8e6}
 L = 196
 N_INPUT_SETS = 3      # distinct input batches rotated between steps (plus 419 MB of class edges streamed per step)
 

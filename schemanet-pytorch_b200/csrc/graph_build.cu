@@ -502,6 +502,7 @@ __device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, S &s, in
     // image constants per lane: destination slot of column q = lane + 32 t
     int dst[LC];
     unsigned dupmask = 0;   // bit t: column t of this lane repeats an earlier code (its value is parked, not summed)
+    unsigned colmask = 0;   // bit t: column lane + 32 t exists (q < L)
 #pragma unroll
     for (int t = 0; t < LC; ++t) {
         const int q = lane + kWarp * t;
@@ -510,6 +511,7 @@ __device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, S &s, in
             const int di = s.didx[q];
             d = di < 0 ? s.rank[q] : n + di;
             if (di >= 0) dupmask |= 1u << t;
+            colmask |= 1u << t;
         }
         dst[t] = d;
     }
@@ -573,6 +575,7 @@ __device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, S &s, in
         } else {                        // later positions: running sums continue; duplicates are parked again
 #pragma unroll
             for (int t = 0; t < LC; ++t) {
+                if (!((colmask >> t) & 1u)) continue;   // the shared sink slot is write-only
                 const bool dup = (dupmask >> t) & 1u;
                 const float oa = bufA[dst[t]], og = bufG[dst[t]];
                 bufA[dst[t]] = dup ? x[t] : oa + x[t];

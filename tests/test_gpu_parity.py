@@ -119,6 +119,15 @@ def test_golden_fused_head(name):
     assert np.array_equal(out["ingredients"].cpu().numpy(), g["ingredients"])
     rel_close(out["pred"], g["pred"], what="logits (fused head)")
     assert int(out["graphs"].max_vertices) == int(g["inst_ids_sizes"].max())
+    # the atlas tensors are only materialised on request; the logits do not depend on it
+    assert head.atlas["class_edges"] is None or not head.materialize_atlas
+    rel_close(head.atlas["class_vertices"], g["class_vertices"], 2e-6, "class vertices (fused head)")
+    head2 = SchemaHead(_t(g["vocab"]), *build_modules(g))
+    head2.materialize_atlas = True
+    out2 = head2(_t(g["mid_feat"]), _t(g["attn"]), _t(g["attn_cls"]))
+    assert torch.equal(out2["pred"], out["pred"])
+    rel_close(head2.atlas["class_edges"], g["class_edges"], 2e-6, "class edges (fused head, materialised)")
+    assert np.array_equal(head2.atlas["class_edges"].cpu().numpy() == 0, g["class_edges"] == 0)
 
 
 def test_golden_plain_list_matcher_path():
