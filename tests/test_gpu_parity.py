@@ -130,6 +130,30 @@ def test_golden_fused_head(name):
     assert np.array_equal(head2.atlas["class_edges"].cpu().numpy() == 0, g["class_edges"] == 0)
 
 
+def test_graphed_head_replays_the_eager_result():
+    """GraphedHead (one CUDA graph over both streams) must reproduce the eager head bit for bit, also after the input
+    buffers were refilled in place and after a parameter changed between replays."""
+    from schemanet_b200.head import SchemaHead, GraphedHead
+    g = load_golden("head_tiny_easy")
+    sn, m = build_modules(g)
+    head = SchemaHead(_t(g["vocab"]), sn, m)
+    mid, attn, cls = _t(g["mid_feat"]), _t(g["attn"]), _t(g["attn_cls"])
+    eager = head(mid, attn, cls)["pred"].clone()
+    rel_close(eager, g["pred"], what="logits (eager, before capture)")
+    bufs = (mid.clone(), attn.clone(), cls.clone())
+    gh = GraphedHead(head, *bufs)
+    assert torch.equal(gh.replay()["pred"], eager)
+    # new inputs in the same buffers (a permutation of the batch)
+    perm = torch.randperm(mid.shape[1], generator=torch.Generator().manual_seed(3)).cuda()
+    bufs[0].copy_(mid[:, perm]); bufs[1].copy_(attn[perm]); bufs[2].copy_(cls[perm])
+    assert torch.equal(gh.replay()["pred"], eager[perm])
+    # a parameter update between replays is honoured (the graph holds pointers, not values)
+    with torch.no_grad():
+        m.gnn.fc.bias.add_(0.25)
+    want = head(mid[:, perm].contiguous(), attn[perm].contiguous(), cls[perm].contiguous())["pred"].clone()
+    assert torch.equal(gh.replay()["pred"], want) and not torch.equal(want, eager[perm])
+
+
 def test_golden_plain_list_matcher_path():
     """Matcher fed with ordinary Python lists (not SchemaNet's packed output) takes the packing path."""
     g = load_golden("head_tiny_easy")
