@@ -71,7 +71,9 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     constexpr int KB_ELEMS = kBf16 ? 64 : 32;      // elements per k-block (one 128-byte row)
     using S = DiscTcSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment for the 128-byte-swizzled TMA tiles, as an OFFSET into the shared array: going through uintptr_t makes
+    // the compiler lose the address space and emit 64-bit generic LD/ST for every shared-memory access of the epilogue
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full = (uint64_t *)(smem + S::kBarOffset);
     uint64_t *empty = full + TC_STAGES;
     uint64_t *tmem_full = empty + TC_STAGES;
@@ -149,6 +151,9 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int row_in_tile = wq * 32 + lane;
         float *my_s = cand_s + (half * TC_BM + row_in_tile) * kCandStride;
         int *my_i = cand_i + (half * TC_BM + row_in_tile) * kCandStride;
+        const uint32_t my_base = smem_u32(my_s), my_end = my_base + 4u * kListSlots;
+        constexpr uint32_t kIdxDelta = 2u * TC_BM * kCandStride * 4u;   // byte distance cand_s -> cand_i
+        (void)my_i;
         constexpr int kChunksPerHalf = (BN / 32) / 2;
         const float cmax = sqrtf(__uint_as_float(*a.cmax_bits));
         int as = 0;
@@ -187,12 +192,21 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         if (cmin < m_run - band) cnt = 0;          // every older candidate is now out of reach
                         m_run = fminf(m_run, cmin);
                         const float thr = m_run + band;
+                        // straight-line predicated appends with explicit shared-space stores (the pointers are carved
+                        // from an aligned dynamic-smem base, which the compiler only knows as generic: it emitted 64-bit
+                        // generic ST.E, unconditionally, 64 per chunk and thread).  A store is only issued for an
+                        // actual candidate; slot kListSlots absorbs the stores of a full list.
+                        uint32_t cur = my_base + 4u * (uint32_t)cnt;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            my_s[cnt] = v[j];                       // unconditional store, conditional advance
-                            my_i[cnt] = n_base + j;
-                            cnt = min(cnt + ((v[j] <= thr) ? 1 : 0), kListSlots);   // == kListSlots: list is full
+                            const bool hit = v[j] <= thr;
+                            if (hit) {
+                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(cur), "f"(v[j]) : "memory");
+                                asm volatile("st.shared.s32 [%0], %1;" ::"r"(cur + kIdxDelta), "r"(n_base + j) : "memory");
+                            }
+                            cur = min(cur + (hit ? 4u : 0u), my_end);       // my_end: list is full
                         }
+                        cnt = (int)((cur - my_base) >> 2);
                     }
                 }
                 tc_fence_before();

@@ -118,7 +118,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
     using P = GemmPlan<CTAS>;
     constexpr int S = P::kStages;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment for the 128-byte-swizzled TMA tiles, as an OFFSET into the shared array: going through uintptr_t makes
+    // the compiler lose the address space and emit 64-bit generic LD/ST for every shared-memory access of the epilogue
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full = (uint64_t *)(smem + P::kBar);
     uint64_t *empty = full + S;
     uint64_t *tmem_full = empty + S;
