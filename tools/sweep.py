@@ -28,8 +28,9 @@ dev = torch.device("cuda")
 STAGES = {"discretize": ("rows_to_bf16_kernel", "codebook_norms_kernel", "row_sqnorm_kernel", "discretize_tc_kernel",
                          "discretize_tc_bf16_kernel", "discretize_exact_kernel", "discretize_recheck_kernel"),
           "graph": ("instance_graph_kernel",),
-          "match": ("gnn_adj_prep", "gnn_embed_gather", "gnn_split_weights", "gnn_adj_gemm_tc", "gnn_linear_ln_tc",
-                    "gnn_pool_rows", "gnn_pool_fc", "similarity_kernel", "gnn_adj_gemm", "gnn_linear_gemm", "ln_relu_kernel")}
+          "match": ("gnn_adj_prep", "gnn_embed_gather", "gnn_embed_table_linear", "gnn_split_weights", "gnn_adj_gemm_tc",
+                    "gnn_adj_ln_tc", "gnn_linear_ln_tc", "gnn_linear_tc", "gnn_ln_relu_wide", "gnn_pool_rows", "gnn_pool_fc",
+                    "similarity_kernel", "gnn_adj_gemm", "gnn_linear_gemm", "ln_relu_kernel")}
 lines = ["# Stage sweep on B200 (d=384, K=100, D=256; class side cached; images/s per stage)", "",
          "| M | B | discretize us | graph build us | instance match us | discretize Mimg/s | graph Mimg/s | match Mimg/s |",
          "|---|---|---|---|---|---|---|---|"]
