@@ -473,17 +473,6 @@ __device__ __forceinline__ void build_edges(const GraphArgs &a, GraphSmem &s, in
 // The fp32 order per (r1, r2) is exactly the reference's: rows ascending, columns ascending, one running sum
 // (utils.cpp:9).  The epilogue reads all 32 LC slots; those >= n are masked by a zero in the per-lane reciprocal counts.
 
-#ifdef SH_GRAPH_CLOCKS
-__device__ unsigned long long g_clk[8];
-#define CLK(i) do { if ((threadIdx.x & 31) == 0) { long long now_ = clock64(); atomicAdd(&g_clk[i], (unsigned long long)(now_ - t_)); t_ = now_; } } while (0)
-#else
-#define CLK(i)
-#endif
-#ifdef SH_GRAPH_CLOCKS
-#define RCLK(i) do { long long now_ = clock64(); racc_[i - 5] += now_ - tr_; tr_ = now_; } while (0)
-#else
-#define RCLK(i)
-#endif
 template <bool kFromHeads, int LC, class S>
 __device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, S &s, int b, int split, int nsplit)
 {
@@ -544,10 +533,6 @@ __device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, S &s, in
         load_row<kFromHeads, LC>(a, b, info_n & 255, lane, fill, xn);
         load_geo(info_n & 255, gn);
     }
-#ifdef SH_GRAPH_CLOCKS
-    long long tr_ = clock64();
-    long long racc_[3] = {0, 0, 0};
-#endif
     while (k < k_hi) {
         const int info = info_n;
         const int p = info & 255, r1 = (info >> 8) & 255;
@@ -568,7 +553,6 @@ __device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, S &s, in
             }
             warp_softmax<LC>(x, a.clamp_e, use_clamp);
         }
-        RCLK(5);
         if (info & 0x10000) {          // first position of output row r1: plain stores
 #pragma unroll
             for (int t = 0; t < LC; ++t) { bufA[dst[t]] = x[t]; bufG[dst[t]] = g[t]; }
@@ -598,7 +582,6 @@ __device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, S &s, in
             bufG[r] = vg;
         }
         __syncwarp();
-        RCLK(6);
         if (!(info & 0x20000)) continue;   // more positions of r1 follow
 
         // epilogue: block mean, row normalisation, nan_to_num, 2->1 mix.
@@ -633,11 +616,7 @@ __device__ __forceinline__ void build_edges_scatter(const GraphArgs &a, S &s, in
                 if (lane + kWarp * t < n_store)
                     o[kWarp * t] = (lane + kWarp * t < n) ? nan_to_num0(eg[t] / s0) * w0 + nan_to_num0(ea[t] / s1) * w1 : 0.0f;
         }
-        RCLK(7);
     }
-#ifdef SH_GRAPH_CLOCKS
-    if (lane == 0) { atomicAdd(&g_clk[5], (unsigned long long)racc_[0]); atomicAdd(&g_clk[6], (unsigned long long)racc_[1]); atomicAdd(&g_clk[7], (unsigned long long)racc_[2]); }
-#endif
 }
 
 // grid: (image, split) pairs; every CTA ranks the codes of its image and builds 1/nsplit of the edge rows (split 0 also
@@ -649,21 +628,16 @@ __global__ void __launch_bounds__(kWarps * kWarp, kWarps == 8 ? 3 : 2) instance_
     for (int u = blockIdx.x; u < a.B * nsplit; u += gridDim.x) {
         const int b = u / nsplit, split = u % nsplit;
         // the cls row is requested before the (latency-bound) ranking, into warp 0's registers
-#ifdef SH_GRAPH_CLOCKS
-        long long t_ = clock64();
-#endif
         float cls[LC];
         const bool do_vertices = a.vertex_w && split == 0;
         if (do_vertices && threadIdx.x < kWarp) load_cls_row<kFromHeads, LC>(a, b, cls);
         rank_codes(s, a.ingredients + (size_t)b * a.L, a.L);
-        CLK(0);
         const int n = s.n;
         if (threadIdx.x == 0 && split == 0) {
             if (a.num_vertices) a.num_vertices[b] = n;
             if (a.max_vertices) atomicMax(a.max_vertices, n);
         }
         if (do_vertices) build_vertices<kFromHeads, LC>(a, s, b, cls);
-        CLK(1);
         if (a.edges) {
             if (threadIdx.x < kMaxL)
                 s.cinvm[threadIdx.x] = (int)threadIdx.x < n ? ((a.flags & SH_G_SUM) ? 1.0f : 1.0f / (float)s.cnt[threadIdx.x]) : 0.0f;
@@ -673,16 +647,13 @@ __global__ void __launch_bounds__(kWarps * kWarp, kWarps == 8 ? 3 : 2) instance_
                                       (threadIdx.x + 1 == s.start[r + 1] ? 0x20000 : 0);
             }
             __syncthreads();
-            CLK(2);
             build_edges_scatter<kFromHeads, LC>(a, s, b, split, nsplit);
-            CLK(3);
             if (a.flags & SH_G_ZERO_PAD) {   // rows n..L-1 of the [L, L] slot
                 float *o = a.edges + (size_t)b * a.L * a.L;
                 for (int i = n * a.L + split * blockDim.x + threadIdx.x; i < a.L * a.L; i += blockDim.x * nsplit) o[i] = 0.0f;
             }
         }
         __syncthreads();
-        CLK(4);
     }
 }
 
@@ -814,16 +785,6 @@ extern "C" int sh_dev_instance_graphs(const int64_t *ingredients, float *attn, f
     else if (heads) SH_GRAPH_LAUNCH_OCC(true, 8);
     else if (narrow) SH_GRAPH_LAUNCH_OCC(false, 7);
     else SH_GRAPH_LAUNCH_OCC(false, 8);
-#ifdef SH_GRAPH_CLOCKS
-    {
-        unsigned long long h[8];
-        cudaDeviceSynchronize();
-        cudaMemcpyFromSymbol(h, g_clk, sizeof(h));
-        fprintf(stderr, "graph clocks (warp-sum): rank %llu vert %llu setup %llu rows %llu tail %llu | softmax %llu scatter+fold %llu epilogue %llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
-        unsigned long long z[8] = {};
-        cudaMemcpyToSymbol(g_clk, z, sizeof(z));
-    }
-#endif
     SH_CHECK_LAUNCH();
     return 0;
 }

@@ -46,6 +46,7 @@ class SchemaHead:
         self.disc_mode = disc_mode
         self.ws = HeadWorkspace()
         self._class_cache = None
+        self._class_cache_key = None
         # The class side (atlas + class-graph GNN: mostly HBM-bound passes over [K, Vc, Vc]) does not depend on the
         # batch, so it runs on its own stream and overlaps the tensor-core-bound instance side; joined before the logits.
         self.overlap_class_side = True
@@ -66,6 +67,14 @@ class SchemaHead:
         native.discretize(tokens, self.vocab, out_idx=out, idx_rows=bs, idx_row_stride=L, idx_col_stride=1,
                           mode=self.disc_mode)
         return out
+
+    def _class_key(self):
+        sn, gnn = self.schema_net, self.matcher.gnn
+        ts = [sn.vertex_weights.tensor, sn.edge_weights.tensor, sn.class_ingredients.tensor] + list(gnn.parameters())
+        return tuple((id(t), t.data_ptr(), t._version) for t in ts) + (sn.prune_node_threshold, sn.remove_self_loop)
+
+    def invalidate_class_cache(self):
+        self._class_cache, self._class_cache_key = None, None
 
     # -- stage 3, class side ---------------------------------------------------------------------------------------
     def class_features(self) -> torch.Tensor:
@@ -122,6 +131,14 @@ class SchemaHead:
                                sn.edge_attribute_weights.tensor, sn.clamp_vertex_attn, sn.clamp_edge_attn,
                                raw_logits=True, heads=heads, mean=True, out=graphs)
         side = None
+        if cache_class:
+            # the class embeddings are a function of the schema + GNN parameters only; they are reused
+            # while every one of those tensors is the same object at the same version (optimizer steps, load_state_dict
+            # and any other in-place torch op bump the version; writes through .data or raw pointers do not -- call
+            # invalidate_class_cache() after those)
+            key = self._class_key()
+            if key != self._class_cache_key:
+                self._class_cache, self._class_cache_key = None, key
         if cache_class and self._class_cache is not None:
             f_kg = self._class_cache
         elif self.overlap_class_side and self.class_shard is None:

@@ -154,6 +154,29 @@ def test_graphed_head_replays_the_eager_result():
     assert torch.equal(gh.replay()["pred"], want) and not torch.equal(want, eager[perm])
 
 
+def test_class_cache_is_keyed_on_parameter_versions():
+    """cache_class=True reuses the class embeddings only while the schema / GNN parameters are unchanged (f4)."""
+    from schemanet_b200.head import SchemaHead
+    from schemanet_b200 import native
+    g = load_golden("head_tiny_easy")
+    sn, m = build_modules(g)
+    head = SchemaHead(_t(g["vocab"]), sn, m)
+    args = (_t(g["mid_feat"]), _t(g["attn"]), _t(g["attn_cls"]))
+    first = head(*args, cache_class=True)["pred"].clone()
+    n0 = native.launch_count()
+    again = head(*args, cache_class=True)["pred"].clone()
+    cached_launches = native.launch_count() - n0
+    assert torch.equal(first, again)
+    n0 = native.launch_count()
+    head(*args)
+    assert native.launch_count() - n0 > cached_launches           # the class side really was skipped
+    with torch.no_grad():
+        sn.vertex_weights.tensor.mul_(torch.linspace(0.5, 1.5, sn.vertex_weights.tensor.shape[1], device="cuda"))
+    changed = head(*args, cache_class=True)["pred"].clone()        # version bump -> recomputed
+    assert not torch.equal(changed, first)
+    assert torch.equal(changed, head(*args)["pred"])
+
+
 def test_golden_plain_list_matcher_path():
     """Matcher fed with ordinary Python lists (not SchemaNet's packed output) takes the packing path."""
     g = load_golden("head_tiny_easy")
