@@ -267,6 +267,30 @@ def test_instance_graphs_wide_codes_take_the_same_path_result():
         assert eb[i, n:].abs().sum() == 0 and eb[i, :, n:].abs().sum() == 0
 
 
+@pytest.mark.parametrize("side,M,B", [(8, 40, 5), (16, 500, 4), (5, 9, 3)])
+def test_instance_graphs_other_token_counts(side, M, B):
+    """L = 64 / 256 (the 8-columns-per-lane instantiation, L = kMaxL) / 25 tokens against the oracle."""
+    from schemanet_b200 import native
+    L = side * side
+    g = torch.Generator().manual_seed(side)
+    ing = torch.randint(0, M, (B, L), generator=g)
+    attn = 0.5 * torch.randn(B, L, L, generator=g)
+    cls = 0.5 * torch.randn(B, L, generator=g)
+    geo = ho.pair_wise_point_sim(side, side, 1.0, 2.0)
+    wcol = torch.tensor([[0.4], [0.6]])
+    got = native.instance_graphs(ing.cuda(), attn.cuda(), cls.cuda(), geo.cuda(), wcol.cuda(), wcol.cuda(), -0.5, -0.5, zero_pad=True)
+    ref = ho.instance_graphs(ing, attn, cls, wcol, wcol, clamp_vertex=-0.5, clamp_edge=-0.5, feat_h=side, feat_w=side)
+    e = got.edges.view(B, L, L).cpu()
+    for i in range(B):
+        n = int(got.num_vertices[i])
+        assert n == len(ref["instance_ingredients"][i])
+        assert torch.equal(got.ids[i, :n].cpu(), ref["instance_ingredients"][i])
+        rel_close(got.vertex_w[i, :n], ref["instance_vertices"][i], what=f"vertices L={L}")
+        assert torch.equal(e[i, :n, :n] == 0, ref["instance_edges"][i] == 0)
+        rel_close(e[i, :n, :n], ref["instance_edges"][i], what=f"edges L={L}")
+        assert e[i, n:].abs().sum() == 0 and e[i, :, n:].abs().sum() == 0
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # seeded inputs vs the oracle
 # ----------------------------------------------------------------------------------------------------------------
@@ -415,7 +439,8 @@ def test_class_side_large_tile_path():
 
 
 @pytest.mark.parametrize("K,Vc,D,thr,rsl", [(4, 1024, 256, 0.001, False), (3, 500, 256, 0.001, True), (2, 296, 512, 0.0034, False),
-                                            (3, 264, 256, None, False), (2, 301, 256, 0.0033, False)])
+                                            (3, 264, 256, None, False), (2, 301, 256, 0.0033, False),
+                                            (3, 264, 256, 0.5, False)])     # 0.5: every vertex pruned (adjacency = I)
 def test_class_side_fused_equals_atlas_then_gnn(K, Vc, D, thr, rsl):
     """sh_dev_class_side on the tensor-core path feeds the compacted, normalised edges straight into the adjacency
     operand.  It must return bit-identical class embeddings whether or not the full class_edges tensor is asked for,
