@@ -173,6 +173,9 @@ class GraphedHead:
     an optimiser step between replays is honoured."""
 
     def __init__(self, head: "SchemaHead", mid_feat: torch.Tensor, attn: torch.Tensor, attn_cls: torch.Tensor, warmup: int = 2):
+        if head.class_shard is not None:
+            raise RuntimeError("GraphedHead: the class-sharded head issues an NCCL all-gather per step; capture the "
+                               "batch-sharded configuration (class_shard=None) or call the head eagerly")
         self.head, self.inputs = head, (mid_feat, attn, attn_cls)
         for _ in range(max(1, warmup)):          # lazy initialisation (workspaces, function attributes) outside the capture
             head(mid_feat, attn, attn_cls)
