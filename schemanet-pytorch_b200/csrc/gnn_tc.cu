@@ -52,6 +52,12 @@ struct GemmTcArgs {
     // epilogue
     float *out_hi, *out_lo;      // EPI_STORE_SPLIT: Y hi/lo [G, n_fixed, 256]; EPI_LN_RELU_T_SPLIT: H^T hi/lo [G, 256, ldk]
     float *out_rows;             // EPI_LN_RELU_ROWS: H [G*n_fixed, 256]
+    // EPI_LN_RELU_ROWS on flattened rows (G == 1) with pool_groups != null: instead of storing H, emit the vertex-weighted
+    // column sums of every 32-row group, split at the (at most one) graph boundary inside the group:
+    // pool_groups[group, 0 | 1, 256]  (slot 0: rows of the group's first graph, slot 1: rows of the next graph)
+    const float *pool_w;         // [graphs, ld_w] vertex weights
+    int ld_w;
+    float *pool_groups;
     int ldk;                     // row stride of the transposed output
     const float *bias, *gamma, *beta;
     float eps;
@@ -321,7 +327,38 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                         const float z = v[j] + s_bias[n];
                         v[j] = fmaxf((z - mean) * rstd * s_gamma[n] + s_beta[n], 0.0f);
                     }
-                    if (EPI == EPI_LN_RELU_ROWS) {
+                    if (EPI == EPI_LN_RELU_ROWS && a.pool_groups != nullptr) {
+                        // fused weighted pooling (gnn.py:94-95): the activations never go to memory
+                        const int m_warp = mb * G_BM + wq * 32;                       // flattened row of lane 0
+                        const int g0 = m_warp / a.rows_per_graph;
+                        const int split = min(32, (g0 + 1) * a.rows_per_graph - m_warp);   // rows of the group's first graph
+                        const float wrow = valid ? __ldg(a.pool_w + (size_t)gg * a.ld_w + i) : 0.0f;
+                        float *tile = s_out + wq * 32 * 33;
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = v[j] * wrow;
+                        __syncwarp();
+                        float s0 = 0.0f, s1 = 0.0f;
+                        if (split == 32) {       // usual case: one graph in the group; four independent chains, fixed order
+                            float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+#pragma unroll
+                            for (int r = 0; r < 32; r += 4) {
+                                p0 += tile[r * 33 + lane];
+                                p1 += tile[(r + 1) * 33 + lane];
+                                p2 += tile[(r + 2) * 33 + lane];
+                                p3 += tile[(r + 3) * 33 + lane];
+                            }
+                            s0 = (p0 + p1) + (p2 + p3);
+                        } else {
+                            for (int r = 0; r < split; ++r) s0 += tile[r * 33 + lane];
+                            for (int r = split; r < 32; ++r) s1 += tile[r * 33 + lane];
+                        }
+                        if (m_warp < a.M_total) {
+                            float *pg = a.pool_groups + (size_t)(m_warp / 32) * 2 * G_BN + c * 32 + lane;
+                            pg[0] = s0;
+                            pg[G_BN] = s1;
+                        }
+                    } else if (EPI == EPI_LN_RELU_ROWS) {
                         // rows of masked nodes are never read downstream (pooling stops at n_g): store all rows in range
                         const int m_warp = mb * G_BM + wq * 32;
                         const size_t row0 = (a.G > 1 ? (size_t)g * a.rows_per_graph : 0) + m_warp;
@@ -554,6 +591,33 @@ pool_rows_kernel(const float *__restrict__ H, const float *__restrict__ vertex_w
         }
         partial[((size_t)g * chunks + chunk) * D + d] = acc;
     }
+}
+
+// partial[g, 0, d] = sum of the 32-row group sums the last GEMM's epilogue emitted for graph g (+ the table share of the
+// class side's pruned vertices), partial[g, c > 0, d] = 0: the layout pool_fc_kernel consumes.  Groups are summed in
+// ascending row order, so the result does not depend on the launch configuration.
+__global__ void __launch_bounds__(256)
+pool_groups_reduce_kernel(const float *__restrict__ groups, const int32_t *__restrict__ sizes, int n_fixed, int D, int chunks,
+                          float *__restrict__ partial, const float *__restrict__ extra)
+{
+    const int g = blockIdx.x, d = threadIdx.x;
+    if (d >= D) return;
+    const int n_g = sizes ? sizes[g] : n_fixed;
+    float acc = 0.0f;
+    if (n_g > 0) {
+        const int r0 = g * n_fixed, q0 = r0 / 32, q1 = (r0 + n_g - 1) / 32;
+        for (int q = q0; q <= q1; ++q) {
+            const int slot = ((q * 32) / n_fixed == g) ? 0 : 1;      // is g the first or the second graph of the group
+            acc += groups[((size_t)q * 2 + slot) * D + d];
+        }
+    }
+    if (extra) {
+        float e = 0.0f;
+        for (int y = 0; y < kTableSlices; ++y) e += extra[((size_t)g * kTableSlices + y) * D + d];
+        acc += e;
+    }
+    partial[((size_t)g * chunks) * D + d] = acc;
+    for (int c = 1; c < chunks; ++c) partial[((size_t)g * chunks + c) * D + d] = 0.0f;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -911,7 +975,7 @@ bool gnn_tc_supported(int D, int n_fixed)
 struct TcBuffers {
     float *adj_hi, *adj_lo, *xt_hi, *xt_lo, *xt2_hi, *xt2_lo, *y_hi, *y_lo, *w_hi, *w_lo, *h_rows;
     int32_t *n_act, *old_of_new;
-    float *rowinv, *pool_extra;
+    float *rowinv, *pool_extra, *pool_groups;
     int64_t *pid;
     float *pvw;
     int ldk;
@@ -941,6 +1005,7 @@ static TcBuffers carve_tc(void *base, int G, int n_fixed, int D)
     b.old_of_new = (int32_t *)(p + off); off += al256((size_t)G * n_fixed * 4);
     b.rowinv = (float *)(p + off); off += al256((size_t)G * n_fixed * 4);
     b.pool_extra = (float *)(p + off); off += al256((size_t)G * kTableSlices * D * 4);
+    b.pool_groups = (float *)(p + off); off += al256(((size_t)G * n_fixed / 32 + 2) * 2 * D * 4);
     b.pid = (int64_t *)(p + off); off += al256((size_t)G * n_fixed * 8);
     b.pvw = (float *)(p + off); off += al256((size_t)G * n_fixed * 4);
     b.bytes = off;
@@ -1077,6 +1142,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     if (tmap3(&wm2[1], b.w_lo, D, D, 1, D, 0, G_BN / 2)) return 1;
     // node features ping-pong between two X^T buffers (a fused-LayerNorm adjacency GEMM must not overwrite its own B)
     float *xin_hi = b.xt_hi, *xin_lo = b.xt_lo, *xout_hi = b.xt2_hi, *xout_lo = b.xt2_lo;
+    bool pooled_in_epilogue = false;
 
     for (int l = 0; l < p->num_layers; ++l) {
         const bool last = (l == p->num_layers - 1);
@@ -1116,7 +1182,12 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
         CUtensorMap m2[4] = {ym[0], ym[1], wm[0], wm[1]};
         CUtensorMap m2p[4] = {ym[0], ym[1], wm2[0], wm2[1]};
         if (D == G_BN) {
-            if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
+            if (last) {
+                // weighted pooling fused into the epilogue: H of the last layer is never written
+                c.pool_w = vertex_w; c.ld_w = ld_v; c.pool_groups = b.pool_groups;
+                pooled_in_epilogue = true;
+                if (launch_gemm3x<EPI_LN_RELU_ROWS>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1;
+            }
             else { if (launch_gemm3x<EPI_LN_RELU_T_SPLIT>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
         } else {
             // wide embeddings: bias in the GEMM epilogue, LayerNorm + ReLU (+ transpose/split) as a separate pass
@@ -1138,9 +1209,14 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
             SH_CHECK_LAUNCH();
         }
     }
-    dim3 grid(chunks, G);
-    SH_LAUNCH("gnn_pool_rows", st, pool_rows_kernel<<<grid, 256, 0, st>>>(b.h_rows, vertex_w, ld_v, row_sizes, n_fixed, D, chunks, partial,
-                                                                          table_tail ? b.pool_extra : nullptr));
+    if (pooled_in_epilogue) {
+        SH_LAUNCH("gnn_pool_rows", st, pool_groups_reduce_kernel<<<G, 256, 0, st>>>(b.pool_groups, row_sizes, n_fixed, D, chunks, partial,
+                                                                                     table_tail ? b.pool_extra : nullptr));
+    } else {
+        dim3 grid(chunks, G);
+        SH_LAUNCH("gnn_pool_rows", st, pool_rows_kernel<<<grid, 256, 0, st>>>(b.h_rows, vertex_w, ld_v, row_sizes, n_fixed, D, chunks, partial,
+                                                                              table_tail ? b.pool_extra : nullptr));
+    }
     SH_CHECK_LAUNCH();
     return 0;
 }
