@@ -299,23 +299,27 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                 const bool in_range = a.G > 1 ? m < a.rows_per_graph : m < a.M_total;
                 const int n_node = (in_range && a.row_sizes) ? a.row_sizes[gg] : a.rows_per_graph;
                 const bool valid = in_range && i < n_node;
-                float sum = 0.0f;
+                // mean and variance in ONE pass over the accumulator row (each pass is 8 tcgen05.ld + 256 adds per thread, and
+                // the epilogue, not the MMA, bounds these kernels): sums of (z - K) and (z - K)^2 with the shift K = z[0], a
+                // sample of the row itself, so that var = S2/n - (S1/n)^2 subtracts quantities of the size of the variance
+                // (shifted-data algorithm; ~2e-7 relative, the same as the two-pass form at this width)
+                float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f}, shift = 0.0f;   // 4 independent chains each
 #pragma unroll 1
                 for (int c = 0; c < G_BN / 32; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+                    if (c == 0) shift = v[0] + s_bias[0];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sum += v[j] + s_bias[c * 32 + j];
+                    for (int j = 0; j < 32; ++j) {
+                        const float tt = v[j] + s_bias[c * 32 + j] - shift;
+                        p1[j & 3] += tt;
+                        p2[j & 3] = fmaf(tt, tt, p2[j & 3]);
+                    }
                 }
-                const float mean = sum / (float)G_BN;
-                float var = 0.0f;
-#pragma unroll 1
-                for (int c = 0; c < G_BN / 32; ++c) {
-                    float v[32];
-                    tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { const float tt = v[j] + s_bias[c * 32 + j] - mean; var = fmaf(tt, tt, var); }
-                }
+                const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
+                const float dm = s1 / (float)G_BN;
+                const float mean = shift + dm;
+                const float var = fmaxf(s2 - s1 * dm, 0.0f);        // = sum (z - mean)^2
                 const float rstd = 1.0f / sqrtf(var / (float)G_BN + a.eps);
 #pragma unroll 1
                 for (int c = 0; c < G_BN / 32; ++c) {
