@@ -989,7 +989,7 @@ struct TcBuffers {
 static TcBuffers carve_tc(void *base, int G, int n_fixed, int D)
 {
     TcBuffers b{};
-    b.ldk = (n_fixed + 3) / 4 * 4;
+    b.ldk = (n_fixed + 31) / 32 * 32;   // rows of the K-major operands start on 128-byte lines: a TMA box row is one line, not two halves
     char *p = (char *)base;
     size_t off = 0;
     const size_t adj_b = al256((size_t)G * n_fixed * b.ldk * 4), xt_b = al256((size_t)G * D * b.ldk * 4);
