@@ -1095,8 +1095,76 @@ static bool layer0_fused(const sh_gnn_params *p, int G, int n_fixed)
     return p->embed_dim == G_BN && (int64_t)(p->num_codes + 1) <= (int64_t)G * n_fixed;
 }
 
+// The (M+1)-row table work of a forward (layer-0 product P_0, the activation tables of the class side, the pooled share of
+// its pruned vertices) depends on the parameters only -- not on the adjacency operand -- and consists of small,
+// latency-bound kernels.  It is forked onto an auxiliary stream so that it runs under the HBM-bound operand preparation
+// (atlas pass, adjacency prep) instead of in front of the GEMMs, and joined before the first consumer (embed_gather).
+// Fork/join are event dependencies, so the pattern is also valid inside a CUDA-graph capture of `st`.
+struct AuxLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static AuxLane *aux_lane(int which)   // 0: instance-side forwards, 1: class-side forwards (no false dependencies between them)
+{
+    static AuxLane lanes[64][2];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    AuxLane &l = lanes[dev][which];
+    if (l.stream == nullptr) {
+        if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &l;
+}
+
 // table_tail (class side, needs layer0_fused): rows >= row_sizes[g] are pruned vertices; they get no GEMM rows, their
 // pooled contribution comes from the per-code activation tables (see pool_table_rows_kernel).
+// Launches the table work after everything already enqueued on `st` (ids / vertex_w / row_sizes must be ready by then) and
+// returns with it in flight on the auxiliary stream; tables_join() makes `st` wait for it.
+static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_t *row_sizes, const int64_t *ids,
+                        const float *vertex_w, const TcBuffers &b, cudaStream_t st, bool table_tail)
+{
+    const int D = p->embed_dim;
+    if (!layer0_fused(p, G, n_fixed)) return 0;
+    static const bool serial = getenv("SCHEMANET_TABLES_INLINE") != nullptr;
+    AuxLane *lane = serial ? nullptr : aux_lane(table_tail ? 1 : 0);
+    cudaStream_t ts = lane ? lane->stream : st;
+    if (lane) {
+        SH_CHECK_CUDA(cudaEventRecord(lane->fork, st));
+        SH_CHECK_CUDA(cudaStreamWaitEvent(ts, lane->fork, 0));
+    }
+    // P_0 = Emb W_0^T into y_lo; with a table tail the same launch also emits T_0 = relu(LN(P_0 + b_0)) into h_rows
+    if (launch_rows_linear(p->embedding, p->lin_w[0], p->num_codes + 1, D, b.y_lo, ts, p->lin_b[0], p->ln_w[0], p->ln_b[0],
+                           p->ln_eps, table_tail ? b.h_rows : nullptr))
+        return 1;
+    if (table_tail) {
+        // T_l ping-pongs between h_rows and y_hi: both are free until the GEMMs reach them, and the pooled sums of the
+        // pruned vertices are taken (into pool_extra) before that
+        const int rows = p->num_codes + 1;
+        float *cur = b.h_rows, *nxt = b.y_hi;
+        for (int l = 1; l < p->num_layers; ++l) {
+            if (launch_rows_linear(cur, p->lin_w[l], rows, D, nullptr, ts, p->lin_b[l], p->ln_w[l], p->ln_b[l], p->ln_eps, nxt))
+                return 1;
+            float *t = cur; cur = nxt; nxt = t;
+        }
+        SH_LAUNCH("gnn_pool_table_rows", ts, pool_table_rows_kernel<<<dim3(G, kTableSlices), 256, 0, ts>>>(cur, ids, vertex_w, row_sizes, n_fixed, D, b.pool_extra));
+        SH_CHECK_LAUNCH();
+    }
+    if (lane) SH_CHECK_CUDA(cudaEventRecord(lane->join, ts));
+    return 0;
+}
+
+static int tables_join(const sh_gnn_params *p, int G, int n_fixed, cudaStream_t st, bool table_tail)
+{
+    if (!layer0_fused(p, G, n_fixed)) return 0;
+    static const bool serial = getenv("SCHEMANET_TABLES_INLINE") != nullptr;
+    AuxLane *lane = serial ? nullptr : aux_lane(table_tail ? 1 : 0);
+    if (lane) SH_CHECK_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
+    return 0;
+}
+
+// tables_begin() must have been called on `st` before (after the kernels that produce ids / vertex_w / row_sizes).
 static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *k_sizes, int identity_tail,
                          const int32_t *row_sizes, const int64_t *ids, int ld_ids, const float *vertex_w, int ld_v,
                          const TcBuffers &b, int chunks, float *partial, cudaStream_t st, bool table_tail = false)
@@ -1108,27 +1176,8 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     // (still unused) Y_lo buffer, which it fits whenever the batch has at least M+1 node slots.
     const bool fuse0 = layer0_fused(p, G, n_fixed);
     SH_REQUIRE(!table_tail || (fuse0 && row_sizes && !identity_tail), "run_layers_tc: table tail needs the fused layer 0");
-    const float *table = p->embedding;
-    if (fuse0) {
-        // with a table tail the same launch also emits T_0 = relu(LN(P_0 + b_0)) into h_rows (free until the last layer)
-        if (launch_rows_linear(p->embedding, p->lin_w[0], p->num_codes + 1, D, b.y_lo, st, p->lin_b[0], p->ln_w[0], p->ln_b[0],
-                               p->ln_eps, table_tail ? b.h_rows : nullptr))
-            return 1;
-        table = b.y_lo;
-    }
-    if (table_tail) {
-        // T_l ping-pongs between h_rows and y_hi: both are free until the GEMMs below reach them, and the pooled sums of
-        // the pruned vertices are taken (into pool_extra) before that
-        const int rows = p->num_codes + 1;
-        float *cur = b.h_rows, *nxt = b.y_hi;
-        for (int l = 1; l < p->num_layers; ++l) {
-            if (launch_rows_linear(cur, p->lin_w[l], rows, D, nullptr, st, p->lin_b[l], p->ln_w[l], p->ln_b[l], p->ln_eps, nxt))
-                return 1;
-            float *t = cur; cur = nxt; nxt = t;
-        }
-        SH_LAUNCH("gnn_pool_table_rows", st, pool_table_rows_kernel<<<dim3(G, kTableSlices), 256, 0, st>>>(cur, ids, vertex_w, row_sizes, n_fixed, D, b.pool_extra));
-        SH_CHECK_LAUNCH();
-    }
+    const float *table = fuse0 ? b.y_lo : p->embedding;
+    if (tables_join(p, G, n_fixed, st, table_tail)) return 1;
     {
         dim3 grid2(ceil_div(ldk, 32), ceil_div(D, 256), G);
         SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(table, ids, ld_ids, row_sizes, n_fixed, ldk, D, b.xt_hi, b.xt_lo));
@@ -1230,6 +1279,7 @@ int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *si
                    float *partial, void *workspace, cudaStream_t st)
 {
     TcBuffers b = carve_tc(workspace, G, n_fixed, p->embed_dim);
+    if (tables_begin(p, G, n_fixed, sizes, ids, vertex_w, b, st, false)) return 1;
     if (getenv("SCHEMANET_ADJ_TILED") != nullptr) {
         dim3 grid(ceil_div(b.ldk, 32), ceil_div(n_fixed, 32), G);
         SH_LAUNCH("gnn_adj_prep", st, adj_prep_kernel<<<grid, 256, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj_hi, b.adj_lo));
@@ -1266,6 +1316,7 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
               class_perm_kernel<<<K, 1024, 0, st>>>(class_vertices, class_ingredients, Vc, prune_threshold, prune, b.n_act,
                                                     b.old_of_new, b.pid, b.pvw));
     SH_CHECK_LAUNCH();
+    if (tables_begin(p, K, Vc, b.n_act, b.pid, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;
     SH_LAUNCH("class_adj_prep_kernel", st,
               class_adj_prep_kernel<<<dim3(ceil_div(b.ldk, 32), ceil_div(Vc, 32), K), 256, 0, st>>>(
                   class_edges, K, Vc, b.ldk, G_BM * gemm_ctas(), class_table_tail(p, K, Vc) ? 0 : 1, b.n_act, b.old_of_new,
@@ -1288,6 +1339,7 @@ int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc
               class_perm_kernel<<<K, 1024, 0, st>>>(class_vertices, class_ingredients, Vc, prune_threshold, prune, b.n_act,
                                                     b.old_of_new, b.pid, b.pvw));
     SH_CHECK_LAUNCH();
+    if (tables_begin(p, K, Vc, b.n_act, b.pid, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;
     if (launch_class_edges(edge_weights, class_vertices, K, Vc, prune_threshold, prune_in_place, remove_self_loop, class_edges,
                            b.rowinv, st))
         return 1;
