@@ -1122,7 +1122,7 @@ static AuxLane *aux_lane(int which)   // 0: instance-side forwards, 1: class-sid
 // pooled contribution comes from the per-code activation tables (see pool_table_rows_kernel).
 // Launches the table work after everything already enqueued on `st` (ids / vertex_w / row_sizes must be ready by then) and
 // returns with it in flight on the auxiliary stream; tables_join() makes `st` wait for it.
-static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_t *row_sizes, const int64_t *ids,
+static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_t *row_sizes, const int64_t *ids, int ld_ids,
                         const float *vertex_w, const TcBuffers &b, cudaStream_t st, bool table_tail)
 {
     const int D = p->embed_dim;
@@ -1149,6 +1149,13 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
             float *t = cur; cur = nxt; nxt = t;
         }
         SH_LAUNCH("gnn_pool_table_rows", ts, pool_table_rows_kernel<<<dim3(G, kTableSlices), 256, 0, ts>>>(cur, ids, vertex_w, row_sizes, n_fixed, D, b.pool_extra));
+        SH_CHECK_LAUNCH();
+    }
+    {
+        // X_0^T of the fused layer 0 (rows of P_0 gathered by node id): L2-write bound, it also runs under the HBM-read-bound
+        // operand preparation
+        dim3 grid2(ceil_div(b.ldk, 32), ceil_div(D, 256), G);
+        SH_LAUNCH("gnn_embed_gather", ts, embed_gather_t_kernel<<<grid2, 256, 0, ts>>>(b.y_lo, ids, ld_ids, row_sizes, n_fixed, b.ldk, D, b.xt_hi, b.xt_lo));
         SH_CHECK_LAUNCH();
     }
     if (lane) SH_CHECK_CUDA(cudaEventRecord(lane->join, ts));
@@ -1178,7 +1185,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     SH_REQUIRE(!table_tail || (fuse0 && row_sizes && !identity_tail), "run_layers_tc: table tail needs the fused layer 0");
     const float *table = fuse0 ? b.y_lo : p->embedding;
     if (tables_join(p, G, n_fixed, st, table_tail)) return 1;
-    {
+    if (!fuse0) {      // (fused layer 0: already gathered from P_0 by tables_begin)
         dim3 grid2(ceil_div(ldk, 32), ceil_div(D, 256), G);
         SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(table, ids, ld_ids, row_sizes, n_fixed, ldk, D, b.xt_hi, b.xt_lo));
         SH_CHECK_LAUNCH();
@@ -1279,7 +1286,7 @@ int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *si
                    float *partial, void *workspace, cudaStream_t st)
 {
     TcBuffers b = carve_tc(workspace, G, n_fixed, p->embed_dim);
-    if (tables_begin(p, G, n_fixed, sizes, ids, vertex_w, b, st, false)) return 1;
+    if (tables_begin(p, G, n_fixed, sizes, ids, ld_v, vertex_w, b, st, false)) return 1;
     if (getenv("SCHEMANET_ADJ_TILED") != nullptr) {
         dim3 grid(ceil_div(b.ldk, 32), ceil_div(n_fixed, 32), G);
         SH_LAUNCH("gnn_adj_prep", st, adj_prep_kernel<<<grid, 256, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj_hi, b.adj_lo));
@@ -1316,7 +1323,7 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
               class_perm_kernel<<<K, 1024, 0, st>>>(class_vertices, class_ingredients, Vc, prune_threshold, prune, b.n_act,
                                                     b.old_of_new, b.pid, b.pvw));
     SH_CHECK_LAUNCH();
-    if (tables_begin(p, K, Vc, b.n_act, b.pid, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;
+    if (tables_begin(p, K, Vc, b.n_act, b.pid, Vc, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;
     SH_LAUNCH("class_adj_prep_kernel", st,
               class_adj_prep_kernel<<<dim3(ceil_div(b.ldk, 32), ceil_div(Vc, 32), K), 256, 0, st>>>(
                   class_edges, K, Vc, b.ldk, G_BM * gemm_ctas(), class_table_tail(p, K, Vc) ? 0 : 1, b.n_act, b.old_of_new,
@@ -1339,7 +1346,7 @@ int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc
               class_perm_kernel<<<K, 1024, 0, st>>>(class_vertices, class_ingredients, Vc, prune_threshold, prune, b.n_act,
                                                     b.old_of_new, b.pid, b.pvw));
     SH_CHECK_LAUNCH();
-    if (tables_begin(p, K, Vc, b.n_act, b.pid, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;
+    if (tables_begin(p, K, Vc, b.n_act, b.pid, Vc, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;
     if (launch_class_edges(edge_weights, class_vertices, K, Vc, prune_threshold, prune_in_place, remove_self_loop, class_edges,
                            b.rowinv, st))
         return 1;
