@@ -31,6 +31,8 @@ static bool g_prof_on = false;
 static std::vector<ProfRecord> g_prof;
 static std::mutex g_prof_mu;
 
+bool prof_on() { return g_prof_on; }
+
 void prof_begin(const char *name, cudaStream_t st)
 {
     if (!g_prof_on) return;

@@ -14,6 +14,7 @@ void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 
 // Optional per-kernel timing (sh_profile_enable): CUDA events recorded on the launching stream around each launch.
+bool prof_on();   // per-kernel event timing requested (sh_profile_enable): kernels then run one at a time
 void prof_begin(const char *name, cudaStream_t st);
 void prof_end(cudaStream_t st);
 #define SH_LAUNCH(name, stream, ...)          \

@@ -1128,7 +1128,7 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
     const int D = p->embed_dim;
     if (!layer0_fused(p, G, n_fixed)) return 0;
     static const bool serial = getenv("SCHEMANET_TABLES_INLINE") != nullptr;
-    AuxLane *lane = serial ? nullptr : aux_lane(table_tail ? 1 : 0);
+    AuxLane *lane = (serial || prof_on()) ? nullptr : aux_lane(table_tail ? 1 : 0);   // profiling: a kernel's time is its own
     cudaStream_t ts = lane ? lane->stream : st;
     if (lane) {
         SH_CHECK_CUDA(cudaEventRecord(lane->fork, st));
@@ -1166,7 +1166,7 @@ static int tables_join(const sh_gnn_params *p, int G, int n_fixed, cudaStream_t 
 {
     if (!layer0_fused(p, G, n_fixed)) return 0;
     static const bool serial = getenv("SCHEMANET_TABLES_INLINE") != nullptr;
-    AuxLane *lane = serial ? nullptr : aux_lane(table_tail ? 1 : 0);
+    AuxLane *lane = (serial || prof_on()) ? nullptr : aux_lane(table_tail ? 1 : 0);   // profiling: a kernel's time is its own
     if (lane) SH_CHECK_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
     return 0;
 }
