@@ -5,6 +5,7 @@ import importlib.util
 import os
 import re
 import subprocess
+import sys
 import sysconfig
 
 import numpy as np
@@ -15,6 +16,7 @@ from conftest import load_golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "schemanet-pytorch_b200", "schemanet_b200")
+MOD = "sh_integration_stub"        # the document's module is called `extension`; renamed here so that it cannot shadow oracle/_ref
 
 
 def _build_stub(tmp):
@@ -23,17 +25,18 @@ def _build_stub(tmp):
     code = re.search(r"```cpp\n(.*?)```", doc, re.S).group(1)
     src = os.path.join(tmp, "extension.cpp")
     open(src, "w").write(code)
-    out = os.path.join(tmp, "extension" + sysconfig.get_config_var("EXT_SUFFIX"))
+    out = os.path.join(tmp, MOD + sysconfig.get_config_var("EXT_SUFFIX"))
     inc = ce.include_paths() + [sysconfig.get_paths()["include"], os.path.join(ROOT, "include")]
-    cmd = (["g++", "-std=c++17", "-fPIC", "-shared", "-O1", "-DTORCH_EXTENSION_NAME=extension",
+    cmd = (["g++", "-std=c++17", "-fPIC", "-shared", "-O1", "-DTORCH_EXTENSION_NAME=" + MOD,
             "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)] + ["-I" + i for i in inc] +
            [src, "-o", out, "-L" + LIBDIR, "-l:libschemahead.so", "-Wl,-rpath," + LIBDIR] +
            ["-L" + p for p in ce.library_paths()] + ["-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_python"])
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
-    spec = importlib.util.spec_from_file_location("extension", out)
+    spec = importlib.util.spec_from_file_location(MOD, out)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    sys.modules.pop(MOD, None)      # keep the process-wide module table clean (the oracle imports the reference's `extension`)
     return mod
 
 
