@@ -300,15 +300,23 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                 const int n_node = (in_range && a.row_sizes) ? a.row_sizes[gg] : a.rows_per_graph;
                 const bool valid = in_range && i < n_node;
                 // mean and variance in ONE pass over the accumulator row (each pass is 8 tcgen05.ld + 256 adds per thread, and
-                // the epilogue, not the MMA, bounds these kernels): sums of (z - K) and (z - K)^2 with the shift K = z[0], a
-                // sample of the row itself, so that var = S2/n - (S1/n)^2 subtracts quantities of the size of the variance
+                // the epilogue, not the MMA, bounds these kernels): sums of (z - K) and (z - K)^2 with the shift K = the mean of
+                // the row's first 32 features, so that var = S2/n - (S1/n)^2 subtracts quantities of the size of the variance
                 // (shifted-data algorithm; ~2e-7 relative, the same as the two-pass form at this width)
                 float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f}, shift = 0.0f;   // 4 independent chains each
 #pragma unroll 1
                 for (int c = 0; c < G_BN / 32; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-                    if (c == 0) shift = v[0] + s_bias[0];
+                    if (c == 0) {          // shift = mean of the first 32 features (robust against a single outlier)
+                        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            q0 += v[j] + s_bias[j]; q1 += v[j + 1] + s_bias[j + 1];
+                            q2 += v[j + 2] + s_bias[j + 2]; q3 += v[j + 3] + s_bias[j + 3];
+                        }
+                        shift = ((q0 + q1) + (q2 + q3)) * (1.0f / 32.0f);
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float tt = v[j] + s_bias[c * 32 + j] - shift;
