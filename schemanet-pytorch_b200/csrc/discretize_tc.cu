@@ -1,18 +1,20 @@
-// discretize_tc.cu -- stage 1 on the 5th-generation tensor cores: TMA-fed tcgen05 (kind::tf32) GEMM with the
-// distance + argmin fused into the TMEM epilogue, and an exact fp32 re-check of near ties.
+// discretize_tc.cu -- stage 1 on the 5th-generation tensor cores: TMA-fed tcgen05 GEMM (kind::f16 on bf16 copies of the
+// operands by default, kind::tf32 on the fp32 tensors themselves) with the distance + argmin fused into the TMEM epilogue,
+// and an exact fp32 re-check of near ties.
 //
 // Replaces `torch.cdist(seq, vocabulary.weight).argmin(dim=1)` (discretization/discretization.py:65).
 //
 //   scores  s[r, j] = |c_j|^2 - 2 x_r.c_j            (|x_r|^2 is constant per row: irrelevant for the argmin)
-//   coarse  x_r.c_j from tcgen05.mma kind::tf32: fp32 tiles go from HBM to swizzled shared memory by TMA and are fed
-//           to the tensor core as they are (it uses the top 19 bits), fp32 accumulation in tensor memory
-//   epilogue one thread per token row (TMEM lane): running minimum over all N tiles + the list of every codeword
-//           whose coarse score is within `band` of it (band = beta * 2^-10 * |x_r| * max_j |c_j|)
+//   coarse  x_r.c_j from tcgen05.mma: 128-byte-swizzled tiles go from HBM to shared memory by TMA, fp32 accumulation in
+//           tensor memory
+//   epilogue one thread per token row (TMEM lane) and column half: running minimum over all N tiles + the list of every
+//           codeword whose coarse score is within `band` of it (band = beta * eps * |x_r| * max_j |c_j|)
 //   recheck rows with more than one candidate are re-scored in exact fp32 with the reference formula
 //           sqrt(max(|x|^2 + |c|^2 - 2 x.c, 0)), lowest index on ties (the clamp and the sqrt create ties)
 //
-// Warp roles (192 threads, one CTA per SM, persistent over 128-row blocks):
-//   warp 0: TMA producer      warp 1: TMEM allocator + MMA issuer (one elected lane)      warps 2-5: epilogue
+// Warp roles (320 threads, one CTA per SM, persistent over 128-row blocks):
+//   warp 0: TMA producer      warp 1: TMEM allocator + MMA issuer (one elected lane)      warps 2-9: epilogue (two per
+//   TMEM lane quarter, each scanning half of the accumulator's columns; merged through shared memory)
 // Pipelines: a 4-stage shared-memory ring (full/empty mbarriers, slots freed by tcgen05.commit) and a 2-stage TMEM
 // accumulator ring (tmem_full/tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda_bf16.h>

@@ -1,7 +1,8 @@
 // gnn_tc.cu -- stage 3b on tcgen05 tensor cores: fp32-accurate "3xTF32" batched GEMMs with fused epilogues.
 //
 // Replaces the bmm / Linear / LayerNorm / ReLU chain of GraphConv + Layer (schema_inference/graph/gnn.py:20-46) for
-// embed_dim == 256 (every shipped config except ImageNet's 1024, which stays on the fp32 CUDA-core path).
+// embed_dim % 256 == 0, embed_dim <= 1024 (256: everything fused as described below; wider: bias in the GEMM epilogue,
+// LayerNorm + ReLU as a separate pass).  Other widths stay on the fp32 CUDA-core path (gnn.cu).
 //
 // Precision: the north star allows 1e-5 relative error on logits, which plain TF32 (10-bit mantissa) cannot meet.
 // Every fp32 operand x is therefore split as x = hi + lo with hi = x & 0xffffe000 (exactly representable in TF32) and
@@ -16,8 +17,12 @@
 //   linear GEMM  Z     = Y (rows x D, K-major) * W^T with W [D_out, D_in] (K-major), + bias, LayerNorm, ReLU fused in
 //                the TMEM epilogue (one thread owns one full 256-wide row: LayerNorm needs no cross-thread reduction)
 //                -> H^T [D, n] as hi/lo for the next layer's adj GEMM, or H [rows, D] for the pooling.
-// Kernel layout is the same as discretize_tc.cu: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5
-// epilogue; 2-stage 96 KB shared-memory ring, 2-stage 256-column TMEM accumulator ring.
+// Layer 0 is shortened to ONE adjacency GEMM with bias + LayerNorm + ReLU in its epilogue (the first Linear is applied to
+// the (M+1)-row embedding table instead, see run_layers_tc); the last layer's epilogue emits vertex-weighted group sums
+// instead of activations.  Class graphs run on their un-pruned vertices only (class_perm_kernel, per-code tables).
+// Kernel layout: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5 epilogue; CTA pairs (cta_group::2, one
+// UMMA of M = 256 per pair, each CTA stages its 128 A rows and half of the B tile) with a 3-stage 64 KB shared-memory
+// ring per CTA, or single CTAs with a 2-stage 96 KB ring (SCHEMANET_GEMM_CTAS=1); 2-stage 256-column TMEM accumulator ring.
 #include <stdlib.h>
 #include "common.cuh"
 #include "gnn_tc.cuh"
