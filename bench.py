@@ -27,8 +27,9 @@ import torch  # noqa: E402
 
 WORKLOAD = "cfg2"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r01_ncu_full_kernels.txt (ncu --set full, cfg2)
-NCU_TRAFFIC = {"adjacency_gemm": 384.1e6, "discretize": 39.6e6, "graph_build": 41.8e6, "atlas": 423.8e6}
+NCU_TRAFFIC = {"adjacency_gemm": 385.7e6, "discretize": 39.6e6, "graph_build": 42.0e6, "atlas": 428.6e6}
 L = 196
+NCU_CLASS_GEMM_US = 77.9   # gpu__time_duration of that launch in the same capture
 N_INPUT_SETS = 3      # distinct input batches rotated between steps (plus 419 MB of class edges streamed per step)
 
 
@@ -358,6 +359,12 @@ def run_gpu_arm(args):
                     "peak_source": peaks["source"] + " bf16 sustained / 2 (TF32-equivalent)",
                     "dense_equivalent_tflops": dense / t_dom / 1e12,
                     "tensor_pipe_frac": 3 * ach / peak if tensor_path else None,
+                    # the same launch seen from the memory side (ncu --set full, profiles/r01_ncu_full_kernels.txt): the hi/lo
+                    # fp32 operands make the class-side launch as much an HBM kernel as a tensor kernel
+                    "hbm_view": ({"dram_bytes_per_launch": NCU_TRAFFIC["adjacency_gemm"], "us_per_launch_ncu": NCU_CLASS_GEMM_US,
+                                  "achieved_GBps": NCU_TRAFFIC["adjacency_gemm"] / NCU_CLASS_GEMM_US / 1e3,
+                                  "frac_of_measured_hbm": NCU_TRAFFIC["adjacency_gemm"] / NCU_CLASS_GEMM_US / 1e3 / peaks["hbm_gbs"]}
+                                 if WORKLOAD == "cfg2" and tensor_path else None),
                     "note": ("3xTF32 on tcgen05: `achieved` counts each fp32 multiply-add of the visited tiles once; the "
                              "tensor cores execute 3 TF32 MMAs per product (tensor_pipe_frac = 3 x frac), so frac <= 1/3 "
                              "by construction" if tensor_path else "fp32 CUDA-core FMA path")}
