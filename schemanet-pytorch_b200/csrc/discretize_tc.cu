@@ -51,10 +51,10 @@ struct DiscTcArgs {
     int *cand_idx;         // [R, kCandSlots]
 };
 
-template <int BN>
+template <int BN, int CTAS = 1>
 struct DiscTcSmem {
     static constexpr int kABytes = TC_BM * TC_BK * 4;
-    static constexpr int kBBytes = BN * TC_BK * 4;
+    static constexpr int kBBytes = (BN / CTAS) * TC_BK * 4;     // a CTA pair stages half of the codebook tile each
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = TC_STAGES * kStageBytes;
     static constexpr int kCandOffset = kBarOffset + 256;
@@ -66,12 +66,19 @@ struct DiscTcSmem {
 // kBf16: operands are bf16 copies (64 elements per 128-byte swizzle row, kind::f16, UMMA K = 16) instead of the fp32
 // tensors themselves (32 elements per row, kind::tf32, UMMA K = 8).  Same tile bytes and MMA count per k-block; half the
 // k-blocks, i.e. half the L2->SM operand traffic this kernel is bound by, at twice the tensor rate.
-template <int BN, bool kBf16>
+// CTAS = 2 (opt-in, SCHEMANET_DISC_CTAS=2): CTA pairs (cta_group::2).  One UMMA of M = 256 covers the 128-row blocks of both
+// CTAs; each CTA stages its own A rows and HALF of the codebook tile, which cuts the L2->SM operand traffic per flop by a
+// third.  Measured on B200 (r01): parity-green but no faster (cfg2 100 vs 94 us per call, B=512 d=768 M=1024 246 vs 236 us,
+// ImageNet shape 1272 vs 1291 TFLOP/s) -- the 9 TB/s of operand traffic at cfg2 is not the limiter; the sampled stalls
+// are the MMA <-> epilogue hand-offs of 3 K-cycle tiles (two accumulators).  Same protocol as gemm3x_kernel (gnn_tc.cu):
+// TMA bytes of both CTAs complete on the leader's `full` barrier, tcgen05.commit multicasts to both CTAs' `empty` /
+// `tmem_full` barriers, the peer's epilogue arrives remotely on the leader's `tmem_empty`.
+template <int BN, bool kBf16, int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DiscTcArgs a)
 {
     constexpr int KB_ELEMS = kBf16 ? 64 : 32;      // elements per k-block (one 128-byte row)
-    using S = DiscTcSmem<BN>;
+    using S = DiscTcSmem<BN, CTAS>;
     extern __shared__ uint8_t smem_raw[];
     // 1 KB alignment for the 128-byte-swizzled TMA tiles, as an OFFSET into the shared array: going through uintptr_t makes
     // the compiler lose the address space and emit 64-bit generic LD/ST for every shared-memory access of the epilogue
@@ -87,15 +94,19 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int *half_c = (int *)(half_m + 2 * TC_BM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;      // 0 = the CTA that issues the MMAs
+    const int unit = (int)blockIdx.x / CTAS, num_units = (int)gridDim.x / CTAS;
+    const int num_p_blocks = (a.num_m_blocks + CTAS - 1) / CTAS;  // work items: one 128-row block per CTA of the unit
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], TC_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], TC_EPI_WARPS * CTAS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);
+    if (CTAS == 2) cluster_sync();       // the peer's barriers must exist before anything signals them
+    if (warp == 1) { if (CTAS == 2) tmem_alloc_pair(tmem_ptr, 2 * BN); else tmem_alloc(tmem_ptr, 2 * BN); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -106,23 +117,33 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int mb = blockIdx.x; mb < a.num_m_blocks; mb += gridDim.x)
+            for (int pb = unit; pb < num_p_blocks; pb += num_units) {
+                const int mb = pb * CTAS + rank;           // (a row block past the end loads zero rows: TMA OOB fill)
                 for (int nb = 0; nb < a.num_n_blocks; ++nb)
                     for (int kb = 0; kb < a.num_k_blocks; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t *sa = smem + stage * S::kStageBytes;
-                        mbar_arrive_expect_tx(&full[stage], S::kStageBytes);
-                        tma_load_2d(sa, &tmA, &full[stage], kb * KB_ELEMS, mb * TC_BM);
-                        tma_load_2d(sa + S::kABytes, &tmB, &full[stage], kb * KB_ELEMS, nb * BN);
+                        if (CTAS == 1) {
+                            mbar_arrive_expect_tx(&full[stage], S::kStageBytes);
+                            tma_load_2d(sa, &tmA, &full[stage], kb * KB_ELEMS, mb * TC_BM);
+                            tma_load_2d(sa + S::kABytes, &tmB, &full[stage], kb * KB_ELEMS, nb * BN);
+                        } else {
+                            // both CTAs' bytes complete on the LEADER's barrier (the only one the MMA issuer waits on)
+                            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * S::kStageBytes);
+                            tma_load_2d_pair(sa, &tmA, lead_full, kb * KB_ELEMS, mb * TC_BM);
+                            tma_load_2d_pair(sa + S::kABytes, &tmB, lead_full, kb * KB_ELEMS, nb * BN + rank * (BN / 2));
+                        }
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = kBf16 ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN);
+        constexpr uint32_t idesc = kBf16 ? make_idesc_bf16(TC_BM * CTAS, BN) : make_idesc_tf32(TC_BM * CTAS, BN);
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
-        for (int mb = blockIdx.x; mb < a.num_m_blocks; mb += gridDim.x)
+        for (int pb = unit; pb < num_p_blocks && rank == 0; pb += num_units)
             for (int nb = 0; nb < a.num_n_blocks; ++nb) {
                 mbar_wait(&tmem_empty[as], aphase ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
@@ -135,11 +156,22 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         const uint64_t da = make_desc_k_sw128(sa), db = make_desc_k_sw128(sa + S::kABytes);
 #pragma unroll
                         for (int k = 0; k < ((a.debug & 2) ? 0 : 4); ++k) {   // one UMMA consumes 32 bytes of K (8 tf32 / 16 bf16) of the 128-byte row
-                            if (kBf16) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                            else umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                            const uint64_t ak = da + (uint64_t)(2 * k), bk = db + (uint64_t)(2 * k);
+                            if (CTAS == 1) {
+                                if (kBf16) umma_bf16(tmem_d, ak, bk, idesc, (kb | k) != 0);
+                                else umma_tf32(tmem_d, ak, bk, idesc, (kb | k) != 0);
+                            } else {
+                                if (kBf16) umma_bf16_pair(tmem_d, ak, bk, idesc, (kb | k) != 0);
+                                else umma_tf32_pair(tmem_d, ak, bk, idesc, (kb | k) != 0);
+                            }
                         }
-                        umma_commit(&empty[stage]);          // slot is free once these MMAs have read it
-                        if (kb == a.num_k_blocks - 1) umma_commit(&tmem_full[as]);
+                        if (CTAS == 1) {
+                            umma_commit(&empty[stage]);          // slot is free once these MMAs have read it
+                            if (kb == a.num_k_blocks - 1) umma_commit(&tmem_full[as]);
+                        } else {
+                            umma_commit_pair(&empty[stage], 3);  // frees the slot in both CTAs
+                            if (kb == a.num_k_blocks - 1) umma_commit_pair(&tmem_full[as], 3);
+                        }
                     }
                     __syncwarp();
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -160,7 +192,8 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const float cmax = sqrtf(__uint_as_float(*a.cmax_bits));
         int as = 0;
         uint32_t aphase = 0;
-        for (int mb = blockIdx.x; mb < a.num_m_blocks; mb += gridDim.x) {
+        for (int pb = unit; pb < num_p_blocks; pb += num_units) {
+            const int mb = pb * CTAS + rank;
             const int64_t row = (int64_t)mb * TC_BM + row_in_tile;
             const bool valid = row < a.R;
             const float band = valid ? a.beta * (kBf16 ? 3.90625e-3f : 9.765625e-4f) * sqrtf(a.xn[row]) * cmax : 0.0f;
@@ -213,7 +246,10 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (lane == 0) {
+                    if (CTAS == 1) mbar_arrive(&tmem_empty[as]);
+                    else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));   // the leader owns the accumulator ring
+                }
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
             // merge the two column halves of each row: half 1 publishes its minimum / count, half 0 finalises
@@ -252,7 +288,8 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+    if (CTAS == 2) cluster_sync();       // the peer may still be reading this CTA's shared memory / signalling its barriers
+    if (warp == 1) { if (CTAS == 2) tmem_dealloc_pair(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN); }
 }
 
 // Exact fp32 re-check of the rows the tensor-core pass could not decide (one warp per row).
@@ -341,20 +378,50 @@ int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws,
     return 0;
 }
 
+template <int BN, bool kBf16, int CTAS>
+static int launch_tc_n(const CUtensorMap &tmA, const CUtensorMap &tmB, const DiscTcArgs &a, cudaStream_t st)
+{
+    using S = DiscTcSmem<BN, CTAS>;
+    static bool configured = false;
+    if (!configured) {
+        SH_CHECK_CUDA(cudaFuncSetAttribute(discretize_tc_kernel<BN, kBf16, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        configured = true;
+    }
+    const int units = (a.num_m_blocks + CTAS - 1) / CTAS;
+    const int num_units = min(units, sm_count() / CTAS);
+    const char *name = kBf16 ? "discretize_tc_bf16_kernel" : "discretize_tc_kernel";
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(num_units * CTAS);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = S::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    prof_begin(name, st);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, discretize_tc_kernel<BN, kBf16, CTAS>, tmA, tmB, a);
+    prof_end(st);
+    if (e != cudaSuccess) { set_error("%s launch -> %s", name, cudaGetErrorString(e)); return 1; }
+    SH_CHECK_LAUNCH();
+    return 0;
+}
+
+// SCHEMANET_DISC_CTAS=2 selects CTA pairs (the codebook tile map must then have a box of BN / 2 rows)
+static int disc_ctas()
+{
+    static const int c = [] { const char *e = getenv("SCHEMANET_DISC_CTAS"); return (e && atoi(e) == 2) ? 2 : 1; }();
+    return c;
+}
+
 template <int BN, bool kBf16>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const DiscTcArgs &a, cudaStream_t st)
 {
-    using S = DiscTcSmem<BN>;
-    static bool configured = false;
-    if (!configured) {
-        SH_CHECK_CUDA(cudaFuncSetAttribute(discretize_tc_kernel<BN, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-        configured = true;
-    }
-    const int grid = min(a.num_m_blocks, sm_count());
-    SH_LAUNCH(kBf16 ? "discretize_tc_bf16_kernel" : "discretize_tc_kernel", st,
-              discretize_tc_kernel<BN, kBf16><<<grid, TC_THREADS, S::kTotal, st>>>(tmA, tmB, a));
-    SH_CHECK_LAUNCH();
-    return 0;
+    if (disc_ctas() == 2 && BN >= 128) return launch_tc_n<BN, kBf16, 2>(tmA, tmB, a, st);
+    return launch_tc_n<BN, kBf16, 1>(tmA, tmB, a, st);
 }
 
 // bf16 row-major [rows, cols]: box {64 bf16 (128 B), box_rows}
@@ -378,6 +445,7 @@ int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M
 {
     SH_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)C % 16 == 0), "discretize: tensor-core path needs 16-byte aligned inputs");
     const int BN = M > 128 ? 256 : (M > 64 ? 128 : 64);
+    const int b_split = (disc_ctas() == 2 && BN >= 128) ? 2 : 1;   // CTA pairs stage half of the codebook tile each
     CUtensorMap tmA, tmB;
     if (bf16) {
         // one pass over the tokens produces the bf16 copy and |x|^2 (the fp32 path needs that pass for |x|^2 anyway)
@@ -387,10 +455,10 @@ int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M
         SH_LAUNCH("rows_to_bf16_kernel", st, rows_to_bf16_kernel<<<g2, 256, 0, st>>>(C, M, d, ws.cb, nullptr));
         SH_CHECK_LAUNCH();
         if (make_tmap_bf16(&tmA, ws.xb, (uint64_t)d, (uint64_t)R, TC_BM)) return 1;
-        if (make_tmap_bf16(&tmB, ws.cb, (uint64_t)d, (uint64_t)M, (uint32_t)BN)) return 1;
+        if (make_tmap_bf16(&tmB, ws.cb, (uint64_t)d, (uint64_t)M, (uint32_t)(BN / b_split))) return 1;
     } else {
         if (make_tmap_f32(&tmA, X, (uint64_t)d, (uint64_t)R, 1, (uint64_t)d, 0, TC_BM)) return 1;
-        if (make_tmap_f32(&tmB, C, (uint64_t)d, (uint64_t)M, 1, (uint64_t)d, 0, (uint32_t)BN)) return 1;
+        if (make_tmap_f32(&tmB, C, (uint64_t)d, (uint64_t)M, 1, (uint64_t)d, 0, (uint32_t)(BN / b_split))) return 1;
         if (launch_row_sqnorm(X, R, d, ws.xn, st)) return 1;
     }
     DiscTcArgs a{};
