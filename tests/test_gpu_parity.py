@@ -4,6 +4,9 @@ the oracle on seeded inputs, and -- at BASELINE.json's full sizes -- through siz
 Bars (north star): codeword indices, vertex ids and zero patterns bit-exact; vertex weights, edge weights and logits
 within 1e-5 relative (fp32 accumulation).  `rel_close` measures max|a-b| / max|ref| per tensor.
 """
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -336,6 +339,16 @@ def test_discretize_tensor_core_vs_exact_path(B, d, M, mode, operands):
         assert bool((gap < 1e-6).all()), f"{len(bad)} mismatches on unambiguous rows (largest gap {gap.max():.2e})"
     assert len(bad) <= max(1, flat.shape[0] // 2000)
     assert stats["overflow_rows"] <= flat.shape[0] // 100
+
+
+def test_discretize_cta_pair_variant():
+    """SCHEMANET_DISC_CTAS=2 (cta_group::2 pairs, read once per process) must return the same indices: the tensor-core vs
+    exact-path cases are re-run in a child process with the variant selected."""
+    import subprocess
+    env = dict(os.environ, SCHEMANET_DISC_CTAS="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                        "tensor_core_vs_exact_path or discretize_vs_oracle"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
 
 
 def test_discretize_edge_cases():
