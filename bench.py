@@ -150,7 +150,7 @@ def run_reference_arm(args):
     cpu_head_time(c, vocab, sets, schema, gnn, 1, batch=B)
     t0 = time.perf_counter()
     ips, med, cores, kind = cpu_head_time(c, vocab, sets, schema, gnn, max(1, min(args.steps, 5)), batch=B)
-    sample = (f"full {B}-image cfg2 batch per step, K={c['K']} class side recomputed per step, 1 warm-up + "
+    sample = (f"full {B}-image {WORKLOAD} batch per step, K={c['K']} class side recomputed per step, 1 warm-up + "
               f"{max(1, min(args.steps, 5))} timed steps; native loops = {'reference C++ (oracle/_ref)' if kind == 'reference' else 'oracle C restatement'},"
               f" ATen CPU ops for cdist/bmm/linear/layer_norm with {cores} threads; median of the timed steps")
     line = {"impl": "reference", "metric": "schema_head_images_per_sec", "value": ips, "unit": "images/s",
@@ -407,7 +407,7 @@ def run_gpu_arm(args):
             cpu_head_time(c, vocab, sets, schema, gnn, 1, batch=Bs)
             ips, med, cores, kind = cpu_head_time(c, vocab, sets, schema, gnn, 3, batch=Bs)
             cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
-                   "sample": f"the full {Bs}-image cfg2 batch, K={c['K']} class side recomputed, 1 warm-up + median of 3 steps "
+                   "sample": f"the full {Bs}-image {WORKLOAD} batch, K={c['K']} class side recomputed, 1 warm-up + median of 3 steps "
                              f"({med:.2f} s/step); native loops: "
                              f"{'reference C++ (oracle/_ref)' if kind == 'reference' else 'oracle C restatement'}"}
         line = {"metric": "schema_head_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
