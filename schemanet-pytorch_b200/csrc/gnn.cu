@@ -417,8 +417,10 @@ extern "C" int sh_dev_gnn_forward(const sh_gnn_params *p, int G, int n_fixed, co
     const bool tensor_path = gnn_tc_supported(D, n_fixed) && getenv("SCHEMANET_GNN_SIMT") == nullptr;
     if (tensor_path) {
         char *tc_ws = ws + 2 * slab + align_up((size_t)G * chunks * D * sizeof(float), 256) + align_up((size_t)G * D * sizeof(float), 256);
+        TcFinal fin{out, mean_div, false};
         if (gnn_forward_tc(p, G, n_fixed, sizes, ids, vertex_w, ld_v, edges, edge_batch_stride, edge_ld, chunks, partial,
-                           tc_ws, st)) return 1;
+                           tc_ws, st, &fin)) return 1;
+        if (fin.done) return 0;
     }
     for (int l = 0; l < p->num_layers && !tensor_path; ++l) {
         // Y = ((E + E^T)/2 + I) X          (gnn.py:27-30); layer 0 gathers X from the embedding table (:91)
@@ -481,9 +483,11 @@ extern "C" int sh_dev_class_side(const sh_gnn_params *p, const float *vertex_wei
     char *ws = (char *)workspace;
     float *partial = (float *)(ws + 2 * slab);
     char *tc_ws = ws + 2 * slab + align_up((size_t)K * chunks * D * sizeof(float), 256) + align_up((size_t)K * D * sizeof(float), 256);
+    TcFinal fin{feat_class, nullptr, false};
     if (gnn_class_side_tc(p, edge_weights, K, Vc, prune_threshold, prune_in_place, remove_self_loop, class_vertices, class_edges,
-                          class_ingredients, chunks, partial, tc_ws, st))
+                          class_ingredients, chunks, partial, tc_ws, st, &fin))
         return 1;
+    if (fin.done) return 0;
     return launch_pool_fc(p, partial, K, chunks, Vc, nullptr, feat_class, st);
 }
 
@@ -506,8 +510,10 @@ extern "C" int sh_dev_gnn_forward_class(const sh_gnn_params *p, int K, int Vc, c
     char *ws = (char *)workspace;
     float *partial = (float *)(ws + 2 * slab);
     char *tc_ws = ws + 2 * slab + align_up((size_t)K * chunks * D * sizeof(float), 256) + align_up((size_t)K * D * sizeof(float), 256);
-    if (gnn_class_forward_tc(p, K, Vc, class_vertices, class_edges, class_ingredients, prune_threshold, chunks, partial, tc_ws, st))
+    TcFinal fin{feat_class, nullptr, false};
+    if (gnn_class_forward_tc(p, K, Vc, class_vertices, class_edges, class_ingredients, prune_threshold, chunks, partial, tc_ws, st, &fin))
         return 1;
+    if (fin.done) return 0;
     return launch_pool_fc(p, partial, K, chunks, Vc, nullptr, feat_class, st);
 }
 

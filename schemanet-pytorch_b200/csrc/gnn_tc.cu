@@ -637,6 +637,42 @@ pool_groups_reduce_kernel(const float *__restrict__ groups, const int32_t *__res
     for (int c = 1; c < chunks; ++c) partial[((size_t)g * chunks + c) * D + d] = 0.0f;
 }
 
+// The same group sum followed by mean + fc (gnn.py:96-97) in one kernel: out[g, :] = fc(pooled[g] / N).  grid (G, 8): every
+// CTA rebuilds the pooled vector of its graph in shared memory (<= n/32 + 1 group rows) and computes 1/8 of the outputs.
+__global__ void __launch_bounds__(256)
+pool_groups_fc_kernel(const float *__restrict__ groups, const int32_t *__restrict__ sizes, int n_fixed, int D,
+                      const float *__restrict__ extra, const int32_t *__restrict__ mean_div, const float *__restrict__ fc_w,
+                      const float *__restrict__ fc_b, float *__restrict__ out)
+{
+    extern __shared__ float pooled[];
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_g = sizes ? sizes[g] : n_fixed;
+    const float div = (float)(mean_div ? *mean_div : n_fixed);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.0f;
+        if (n_g > 0) {
+            const int r0 = g * n_fixed, q0 = r0 / 32, q1 = (r0 + n_g - 1) / 32;
+            for (int q = q0; q <= q1; ++q) acc += groups[((size_t)q * 2 + (((q * 32) / n_fixed == g) ? 0 : 1)) * D + d];
+        }
+        if (extra) {
+            float e = 0.0f;
+            for (int y = 0; y < kTableSlices; ++y) e += extra[((size_t)g * kTableSlices + y) * D + d];
+            acc += e;
+        }
+        pooled[d] = acc / div;
+    }
+    __syncthreads();
+    const int per = (D + gridDim.y - 1) / gridDim.y;
+    const int o_end = min(D, (int)(blockIdx.y + 1) * per);
+    for (int o = blockIdx.y * per + warp; o < o_end; o += (int)(blockDim.x >> 5)) {
+        const float *w = fc_w + (size_t)o * D;
+        float acc = 0.0f;
+        for (int d = lane; d < D; d += kWarp) acc = fmaf(pooled[d], w[d], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) out[(size_t)g * D + o] = acc + fc_b[o];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // class side: pruned vertices without GEMM rows
 // ---------------------------------------------------------------------------------------------------------------
@@ -1187,7 +1223,8 @@ static int tables_join(const sh_gnn_params *p, int G, int n_fixed, cudaStream_t 
 // tables_begin() must have been called on `st` before (after the kernels that produce ids / vertex_w / row_sizes).
 static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *k_sizes, int identity_tail,
                          const int32_t *row_sizes, const int64_t *ids, int ld_ids, const float *vertex_w, int ld_v,
-                         const TcBuffers &b, int chunks, float *partial, cudaStream_t st, bool table_tail = false)
+                         const TcBuffers &b, int chunks, float *partial, cudaStream_t st, bool table_tail = false,
+                         TcFinal *fin = nullptr)
 {
     const int D = p->embed_dim, ldk = b.ldk;
     // Layer-0 shortcut (embed_dim 256): (Adj X0) W0^T = Adj (X0 W0^T) and X0 = Emb[ids], so the first Linear is applied to
@@ -1282,7 +1319,12 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
             SH_CHECK_LAUNCH();
         }
     }
-    if (pooled_in_epilogue) {
+    if (pooled_in_epilogue && fin != nullptr) {
+        SH_LAUNCH("gnn_pool_fc", st,
+                  pool_groups_fc_kernel<<<dim3(G, G >= 1024 ? 1 : 8), 256, (size_t)D * sizeof(float), st>>>(
+                      b.pool_groups, row_sizes, n_fixed, D, table_tail ? b.pool_extra : nullptr, fin->mean_div, p->fc_w, p->fc_b, fin->out));
+        fin->done = true;
+    } else if (pooled_in_epilogue) {
         SH_LAUNCH("gnn_pool_rows", st, pool_groups_reduce_kernel<<<G, 256, 0, st>>>(b.pool_groups, row_sizes, n_fixed, D, chunks, partial,
                                                                                      table_tail ? b.pool_extra : nullptr));
     } else {
@@ -1296,7 +1338,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
 
 int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *sizes, const int64_t *ids,
                    const float *vertex_w, int ld_v, const float *edges, int64_t edge_batch_stride, int edge_ld, int chunks,
-                   float *partial, void *workspace, cudaStream_t st)
+                   float *partial, void *workspace, cudaStream_t st, TcFinal *fin)
 {
     TcBuffers b = carve_tc(workspace, G, n_fixed, p->embed_dim);
     if (tables_begin(p, G, n_fixed, sizes, ids, ld_v, vertex_w, b, st, false)) return 1;
@@ -1309,7 +1351,7 @@ int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *si
         SH_LAUNCH("gnn_adj_prep", st, adj_sym_kernel<<<G * cpg, 128, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj_hi, b.adj_lo, cpg));
     }
     SH_CHECK_LAUNCH();
-    return run_layers_tc(p, G, n_fixed, sizes, 0, sizes, ids, ld_v, vertex_w, ld_v, b, chunks, partial, st);
+    return run_layers_tc(p, G, n_fixed, sizes, 0, sizes, ids, ld_v, vertex_w, ld_v, b, chunks, partial, st, false, fin);
 }
 
 // The class graphs' layers after the adjacency operand is in place.  embed_dim 256: pruned vertices are served from the
@@ -1317,17 +1359,18 @@ int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *si
 // and let the row blocks of pruned vertices visit just their identity diagonal.
 static bool class_table_tail(const sh_gnn_params *p, int K, int Vc) { return layer0_fused(p, K, Vc); }
 
-static int class_layers_tc(const sh_gnn_params *p, int K, int Vc, const TcBuffers &b, int chunks, float *partial, cudaStream_t st)
+static int class_layers_tc(const sh_gnn_params *p, int K, int Vc, const TcBuffers &b, int chunks, float *partial, cudaStream_t st,
+                           TcFinal *fin)
 {
     if (class_table_tail(p, K, Vc))
-        return run_layers_tc(p, K, Vc, b.n_act, 0, b.n_act, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st, true);
-    return run_layers_tc(p, K, Vc, b.n_act, 1, nullptr, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st);
+        return run_layers_tc(p, K, Vc, b.n_act, 0, b.n_act, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st, true, fin);
+    return run_layers_tc(p, K, Vc, b.n_act, 1, nullptr, b.pid, Vc, b.pvw, Vc, b, chunks, partial, st, false, fin);
 }
 
 // Class side with the graphs compacted to their un-pruned vertices (see class_perm_kernel), from a materialised atlas.
 int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *class_vertices, const float *class_edges,
                          const int64_t *class_ingredients, float prune_threshold, int chunks, float *partial,
-                         void *workspace, cudaStream_t st)
+                         void *workspace, cudaStream_t st, TcFinal *fin)
 {
     TcBuffers b = carve_tc(workspace, K, Vc, p->embed_dim);
     SH_REQUIRE(Vc <= 65535, "class side: Vc too large");
@@ -1342,7 +1385,7 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
                   class_edges, K, Vc, b.ldk, G_BM * gemm_ctas(), class_table_tail(p, K, Vc) ? 0 : 1, b.n_act, b.old_of_new,
                   b.adj_hi, b.adj_lo));
     SH_CHECK_LAUNCH();
-    return class_layers_tc(p, K, Vc, b, chunks, partial, st);
+    return class_layers_tc(p, K, Vc, b, chunks, partial, st, fin);
 }
 
 // Stage 3a + class side fused (sh_dev_class_side on the tensor-core path): the atlas pass leaves the per-row normalisers,
@@ -1350,7 +1393,8 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
 // [K, Vc, Vc] class_edges tensor is only written when the caller asks for it (class_edges != null) and never read back.
 int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc, float prune_threshold, int prune_in_place,
                       int remove_self_loop, const float *class_vertices, float *class_edges,
-                      const int64_t *class_ingredients, int chunks, float *partial, void *workspace, cudaStream_t st)
+                      const int64_t *class_ingredients, int chunks, float *partial, void *workspace, cudaStream_t st,
+                      TcFinal *fin)
 {
     TcBuffers b = carve_tc(workspace, K, Vc, p->embed_dim);
     SH_REQUIRE(Vc <= 65535, "class side: Vc too large");
@@ -1376,7 +1420,7 @@ int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc
                                                                            b.n_act, b.old_of_new, b.adj_hi, b.adj_lo, cpc));
         SH_CHECK_LAUNCH();
     }
-    return class_layers_tc(p, K, Vc, b, chunks, partial, st);
+    return class_layers_tc(p, K, Vc, b, chunks, partial, st, fin);
 }
 
 }  // namespace sh

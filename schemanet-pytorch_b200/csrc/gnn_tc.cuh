@@ -5,21 +5,31 @@
 namespace sh {
 
 bool gnn_tc_supported(int D, int n_fixed);
+
+// Where the final [G, D] features go.  When the pooling was fused into the last GEMM's epilogue the tensor-core path also
+// applies mean + fc itself (one kernel instead of reduce + pool_fc) and sets `done`; otherwise the caller finishes from
+// `partial` with pool_fc_kernel.
+struct TcFinal {
+    float *out;
+    const int32_t *mean_div;
+    bool done;
+};
 size_t gnn_tc_workspace_bytes(int G, int n_fixed, int D, int chunks);
 // Runs all GNN layers on the tensor cores and leaves the vertex-weighted pooling partials [G, chunks, D] in `partial`.
 int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *sizes, const int64_t *ids,
                    const float *vertex_w, int ld_v, const float *edges, int64_t edge_batch_stride, int edge_ld, int chunks,
-                   float *partial, void *workspace, cudaStream_t st);
+                   float *partial, void *workspace, cudaStream_t st, TcFinal *fin = nullptr);
 
 // Class-side variant: graphs are compacted to their un-pruned vertices first (exact, see gnn_tc.cu).
 int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *class_vertices, const float *class_edges,
                          const int64_t *class_ingredients, float prune_threshold, int chunks, float *partial,
-                         void *workspace, cudaStream_t st);
+                         void *workspace, cudaStream_t st, TcFinal *fin = nullptr);
 
 // sh_dev_class_side on the tensor-core path: atlas edges + class-graph GNN with the un-pruned vertices compacted on the fly
 int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc, float prune_threshold, int prune_in_place,
                       int remove_self_loop, const float *class_vertices, float *class_edges,
-                      const int64_t *class_ingredients, int chunks, float *partial, void *workspace, cudaStream_t st);
+                      const int64_t *class_ingredients, int chunks, float *partial, void *workspace, cudaStream_t st,
+                      TcFinal *fin = nullptr);
 
 // atlas.cu
 int launch_class_vertices(const float *vertex_weights, int K, int Vc, float *class_vertices, cudaStream_t st);
