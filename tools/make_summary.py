@@ -25,7 +25,7 @@ out.append(f"\nReference head on the box's host CPU ({n1['cpu_baseline']['cores'
            f"{n1['clocks']['sm_max_mhz']:.0f} MHz, throttle reasons {n1['clocks']['reasons']}.\n")
 out.append(f"Other shapes, one GPU: cfg1 (DeiT-Tiny / CIFAR-10, batch 64) {c1['value']:,.0f} images/s; cfg3 (DeiT-Base / Caltech-101, "
            f"batch 512) {c3['value']:,.0f} images/s; cfg4 (DeiT-Base / ImageNet-1k, batch 1024, all 1000 schemas on one GPU, D = 1024) "
-           f"{c4['value']:,.0f} images/s (cfg3 / cfg4 lines taken earlier in the round).  Stage sweep vocab 256-8192 x batch 1-4096: r01_sweep.md.\n")
+           f"{c4['value']:,.0f} images/s.  Stage sweep vocab 256-8192 x batch 1-4096: r01_sweep.md.\n")
 out += ["## Per-kernel time inside a step (CUDA events on the launching stream, kernels run one at a time; r01_bench_cfg2_n1.json `kernels`)\n",
         "| kernel | launches/step | ms/launch | share of the serialised sum |", "|---|---|---|---|"]
 for name, v in sorted(n1["kernels"].items(), key=lambda kv: -kv[1]["ms_total"]):
