@@ -315,7 +315,7 @@ def run_gpu_arm(args):
         # as gnn_adj_gemm_tc, and as gnn_adj_ln_tc when LayerNorm is fused into its epilogue)
         FAMILY = {"gnn_adj_gemm_tc": "adjacency_gemm", "gnn_adj_ln_tc": "adjacency_gemm", "gnn_adj_gemm": "adjacency_gemm",
                   "gnn_linear_ln_tc": "linear_gemm", "gnn_linear_tc": "linear_gemm", "gnn_linear_gemm": "linear_gemm",
-                  "discretize_tc_kernel": "discretize", "discretize_tc_bf16_kernel": "discretize",
+                  "discretize_tc_kernel": "discretize", "discretize_tc_f16_kernel": "discretize",
                   "discretize_exact_kernel": "discretize", "instance_graph_kernel": "graph_build",
                   "class_edges_kernel": "atlas"}
         fam_ms = {}
@@ -396,7 +396,7 @@ def run_gpu_arm(args):
             t = kern["class_edges_kernel"]["ms_per_launch"] * 1e-3
             stages["atlas"] = {"ms": t * 1e3, "GBps": alg["atlas"]["bytes"] / t / 1e9,
                                "frac_hbm": alg["atlas"]["bytes"] / t / 1e9 / hbm}
-        for name in ("discretize_exact_kernel", "discretize_tc_kernel", "discretize_tc_bf16_kernel"):
+        for name in ("discretize_exact_kernel", "discretize_tc_kernel", "discretize_tc_f16_kernel"):
             if name in kern:
                 t = kern[name]["ms_per_launch"] * 1e-3
                 stages["discretize"] = {"ms": t * 1e3, "TFLOPs": alg["discretize"]["flops"] / t / 1e12, "kernel": name}

@@ -73,14 +73,16 @@ int sh_dev_attention_prologue(const float *extracted, int B, int H, int T, float
  *     flat [R] result: idx_rows = R, idx_row_stride = 1, idx_col_stride = 0;
  *     the head's token-major rows (r = t*bs + b) written straight into the [bs, L] layout of
  *     ingredient_model_wrapper.py:55: idx_rows = bs, idx_row_stride = L, idx_col_stride = 1.
- *   mode: SH_DISC_AUTO picks a tensor-core path when it applies (bf16 if d % 8 == 0, else tf32 if d % 4 == 0);
- *         SH_DISC_EXACT forces the fp32 CUDA-core scan; every mode returns the same indices (fp32 re-check)
+ *   mode: SH_DISC_AUTO picks a tensor-core path when it applies (fp16 operands if d % 8 == 0, else tf32 if d % 4 == 0);
+ *         SH_DISC_EXACT forces the fp32 CUDA-core scan; every mode returns the same indices: the
+ *         tensor-core pass only short-lists candidates inside a worst-case error band (Cauchy-Schwarz on the measured
+ *         operand rounding residuals); the winner is always decided by the fp32 re-check
  *   workspace: sh_discretize_workspace_bytes(R, d, M) bytes of device scratch.
  * ---------------------------------------------------------------------------------------------------------- */
 #define SH_DISC_AUTO 0
 #define SH_DISC_EXACT 1
 #define SH_DISC_TENSOR 2        /* tcgen05 kind::tf32 coarse pass (fp32 tiles fed as they are) + fp32 re-check */
-#define SH_DISC_TENSOR_BF16 3   /* tcgen05 kind::f16 coarse pass on bf16 copies (half the operand traffic) + fp32 re-check */
+#define SH_DISC_TENSOR_F16 3    /* tcgen05 kind::f16 coarse pass on fp16 copies (half the operand traffic) + fp32 re-check */
 size_t sh_discretize_workspace_bytes(int64_t R, int d, int M);
 int sh_dev_discretize(const float *tokens, const float *vocab, int64_t R, int d, int M, int64_t *out_idx,
                       int64_t idx_rows, int64_t idx_row_stride, int64_t idx_col_stride, float *out_seq,

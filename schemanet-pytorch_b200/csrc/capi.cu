@@ -159,20 +159,20 @@ extern "C" int sh_dev_discretize(const float *tokens, const float *vocab, int64_
     SH_REQUIRE(workspace && workspace_bytes >= sh_discretize_workspace_bytes(R, d, M), "discretize: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     DiscWorkspace ws = carve_disc_workspace(workspace, R, M, d);
-    bool tensor = false, bf16 = false;
-    if (mode == SH_DISC_TENSOR || mode == SH_DISC_TENSOR_BF16) {
-        bf16 = mode == SH_DISC_TENSOR_BF16;
-        SH_REQUIRE(discretize_tc_supported(R, d, M, bf16), "discretize: tensor-core path needs d %% %d == 0, d >= 32, M >= 16 (d=%d M=%d)",
-                   bf16 ? 8 : 4, d, M);
+    bool tensor = false, half = false;
+    if (mode == SH_DISC_TENSOR || mode == SH_DISC_TENSOR_F16) {
+        half = mode == SH_DISC_TENSOR_F16;
+        SH_REQUIRE(discretize_tc_supported(R, d, M, half), "discretize: tensor-core path needs d %% %d == 0, d >= 32, M >= 16 (d=%d M=%d)",
+                   half ? 8 : 4, d, M);
         tensor = true;
     } else if (mode == SH_DISC_AUTO) {
-        bf16 = discretize_tc_supported(R, d, M, true);
-        tensor = bf16 || discretize_tc_supported(R, d, M, false);
+        half = discretize_tc_supported(R, d, M, true);
+        tensor = half || discretize_tc_supported(R, d, M, false);
     }
     SH_CHECK_CUDA(cudaMemsetAsync(ws.counters, 0, 256, st));
     if (launch_codebook_norms(vocab, M, d, ws, st)) return 1;
     if (tensor) {
-        if (launch_discretize_tc(tokens, vocab, R, d, M, out_idx, idx_rows, idx_row_stride, idx_col_stride, ws, bf16, st)) return 1;
+        if (launch_discretize_tc(tokens, vocab, R, d, M, out_idx, idx_rows, idx_row_stride, idx_col_stride, ws, half, st)) return 1;
     } else {
         if (launch_discretize_exact(tokens, vocab, ws.cn, R, d, M, out_idx, idx_rows, idx_row_stride, idx_col_stride, st)) return 1;
     }

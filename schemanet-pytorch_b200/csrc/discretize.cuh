@@ -15,13 +15,15 @@ __device__ __forceinline__ float exact_distance(float xn, float cn, float dot)
 constexpr int kCandSlots = 16;   // near-tie candidates kept per row by the tensor-core path
 
 struct DiscWorkspace {
-    unsigned long long *counters;   // [0] rows re-checked, [1] rows whose candidate list overflowed, [2] max |c|^2 bits
+    unsigned long long *counters;   // [0] rows re-checked, [1] rows whose candidate list overflowed,
+                                    // [2] two 32-bit words: bits of max_j |c_j|^2 and of max_j |c_j - fp16(c_j)|^2
     float *cn;                      // [M]  |c_j|^2
     float *xn;                      // [R]  |x_r|^2
+    float *xe;                      // [R]  |x_r - fp16(x_r)|^2 (fp16 tensor-core path)
     int *cand_count;                // [R]
     int *cand_idx;                  // [R, kCandSlots]
-    unsigned short *xb;             // [R, d]  tokens rounded to bf16 (bf16 tensor-core path)
-    unsigned short *cb;             // [M, d]  codebook rounded to bf16
+    unsigned short *xb;             // [R, d]  tokens rounded to fp16 (fp16 tensor-core path)
+    unsigned short *cb;             // [M, d]  codebook rounded to fp16
     size_t bytes;
 };
 
@@ -35,6 +37,7 @@ inline DiscWorkspace carve_disc_workspace(void *base, int64_t R, int M, int d)
     w.counters = (unsigned long long *)(p + off); off += 256;
     w.cn = (float *)(p + off); off += ws_align(sizeof(float) * ((size_t)M + 256));   // +inf padded to the N tile
     w.xn = (float *)(p + off); off += ws_align(sizeof(float) * (size_t)R);
+    w.xe = (float *)(p + off); off += ws_align(sizeof(float) * (size_t)R);
     w.cand_count = (int *)(p + off); off += ws_align(sizeof(int) * (size_t)R);
     w.cand_idx = (int *)(p + off); off += ws_align(sizeof(int) * (size_t)R * kCandSlots);
     w.xb = (unsigned short *)(p + off); off += ws_align(sizeof(unsigned short) * (size_t)R * d);
@@ -51,8 +54,8 @@ int launch_gather(const float *vocab, const int64_t *idx, int64_t idx_rows, int6
 int launch_discretize_exact(const float *X, const float *C, const float *cn, int64_t R, int d, int M, int64_t *out_idx,
                             int64_t idx_rows, int64_t idx_row_stride, int64_t idx_col_stride, cudaStream_t st);
 // tensor-core path (discretize_tc.cu); returns -1 if the shape is not supported by it
-bool discretize_tc_supported(int64_t R, int d, int M, bool bf16);
+bool discretize_tc_supported(int64_t R, int d, int M, bool half);
 int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M, int64_t *out_idx, int64_t idx_rows,
-                         int64_t idx_row_stride, int64_t idx_col_stride, const DiscWorkspace &ws, bool bf16, cudaStream_t st);
+                         int64_t idx_row_stride, int64_t idx_col_stride, const DiscWorkspace &ws, bool half, cudaStream_t st);
 
 }  // namespace sh

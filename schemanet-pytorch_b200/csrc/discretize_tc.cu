@@ -1,4 +1,4 @@
-// discretize_tc.cu -- stage 1 on the 5th-generation tensor cores: TMA-fed tcgen05 GEMM (kind::f16 on bf16 copies of the
+// discretize_tc.cu -- stage 1 on the 5th-generation tensor cores: TMA-fed tcgen05 GEMM (kind::f16 on fp16 copies of the
 // operands by default, kind::tf32 on the fp32 tensors themselves) with the distance + argmin fused into the TMEM epilogue,
 // and an exact fp32 re-check of near ties.
 //
@@ -8,7 +8,11 @@
 //   coarse  x_r.c_j from tcgen05.mma: 128-byte-swizzled tiles go from HBM to shared memory by TMA, fp32 accumulation in
 //           tensor memory
 //   epilogue one thread per token row (TMEM lane) and column half: running minimum over all N tiles + the list of every
-//           codeword whose coarse score is within `band` of it (band = beta * eps * |x_r| * max_j |c_j|)
+//           codeword whose coarse score is within `band` of it.  The band is a worst-case bound, not a statistical one
+//           (DESIGN.md 4.1): with dx = x - x^ and dc_j = c_j - c^_j the operand rounding residuals (measured by the
+//           conversion pass) and g the fp32 accumulation error coefficient of a length-d dot product,
+//               |x.c_j - tc(x^, c^_j)| <= |dx| |c_j| + |x^| |dc_j| + g |x^| |c^_j|  =: e      (Cauchy-Schwarz)
+//           so the exact-score winner lies within 4e of the coarse minimum (2e per score, two scores).
 //   recheck rows with more than one candidate are re-scored in exact fp32 with the reference formula
 //           sqrt(max(|x|^2 + |c|^2 - 2 x.c, 0)), lowest index on ties (the clamp and the sqrt create ties)
 //
@@ -17,7 +21,7 @@
 //   TMEM lane quarter, each scanning half of the accumulator's columns; merged through shared memory)
 // Pipelines: a 4-stage shared-memory ring (full/empty mbarriers, slots freed by tcgen05.commit) and a 2-stage TMEM
 // accumulator ring (tmem_full/tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "discretize.cuh"
@@ -41,9 +45,10 @@ struct DiscTcArgs {
     int d, M;
     int num_m_blocks, num_n_blocks, num_k_blocks;
     const float *cn;       // [M padded to the N tile] |c_j|^2, +inf beyond M
-    const float *xn;       // [R]
-    const unsigned *cmax_bits;   // bit pattern of max_j |c_j|^2
-    float beta;
+    const float *xn;       // [R]  |x_r|^2
+    const float *xe;       // [R]  |x_r - fp16(x_r)|^2 (half operands; unused with tf32 operands)
+    const unsigned *cmax_bits;   // bit patterns of max_j |c_j|^2 and ([1]) max_j |c_j - fp16(c_j)|^2
+    float gamma;           // accumulation error coefficient: |tc dot - exact dot of the rounded operands| <= gamma |x^| |c^|
     int debug;             // bit 0: epilogue skips its compute, bit 1: MMA issuer skips the MMAs (timing experiments)
     int64_t *out_idx;
     int64_t idx_rows, idx_row_stride, idx_col_stride;
@@ -63,9 +68,11 @@ struct DiscTcSmem {
     static constexpr int kTotal = kHalfOffset + 2 * TC_BM * 8 + 1024;   // + slack for 1024-B alignment
 };
 
-// kBf16: operands are bf16 copies (64 elements per 128-byte swizzle row, kind::f16, UMMA K = 16) instead of the fp32
+// kHalf: operands are fp16 copies (64 elements per 128-byte swizzle row, kind::f16, UMMA K = 16) instead of the fp32
 // tensors themselves (32 elements per row, kind::tf32, UMMA K = 8).  Same tile bytes and MMA count per k-block; half the
-// k-blocks, i.e. half the L2->SM operand traffic this kernel is bound by, at twice the tensor rate.
+// k-blocks, i.e. half the L2->SM operand traffic, at twice the tensor rate.  fp16 (11 significant bits) rather than bf16
+// (8): the rigorous candidate band scales with the operand rounding error, and patch tokens / codewords are far inside
+// the fp16 range (values beyond +-65504 saturate; their residual then blows the band up and the row is rescanned exactly).
 // CTAS = 2 (opt-in, SCHEMANET_DISC_CTAS=2): CTA pairs (cta_group::2).  One UMMA of M = 256 covers the 128-row blocks of both
 // CTAs; each CTA stages its own A rows and HALF of the codebook tile, which cuts the L2->SM operand traffic per flop by a
 // third.  Measured on B200 (r01): parity-green but no faster (cfg2 100 vs 94 us per call, B=512 d=768 M=1024 246 vs 236 us,
@@ -73,11 +80,11 @@ struct DiscTcSmem {
 // are the MMA <-> epilogue hand-offs of 3 K-cycle tiles (two accumulators).  Same protocol as gemm3x_kernel (gnn_tc.cu):
 // TMA bytes of both CTAs complete on the leader's `full` barrier, tcgen05.commit multicasts to both CTAs' `empty` /
 // `tmem_full` barriers, the peer's epilogue arrives remotely on the leader's `tmem_empty`.
-template <int BN, bool kBf16, int CTAS>
+template <int BN, bool kHalf, int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DiscTcArgs a)
 {
-    constexpr int KB_ELEMS = kBf16 ? 64 : 32;      // elements per k-block (one 128-byte row)
+    constexpr int KB_ELEMS = kHalf ? 64 : 32;      // elements per k-block (one 128-byte row)
     using S = DiscTcSmem<BN, CTAS>;
     extern __shared__ uint8_t smem_raw[];
     // 1 KB alignment for the 128-byte-swizzled TMA tiles, as an OFFSET into the shared array: going through uintptr_t makes
@@ -140,7 +147,7 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = kBf16 ? make_idesc_bf16(TC_BM * CTAS, BN) : make_idesc_tf32(TC_BM * CTAS, BN);
+        constexpr uint32_t idesc = kHalf ? make_idesc_f16(TC_BM * CTAS, BN) : make_idesc_tf32(TC_BM * CTAS, BN);
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
         for (int pb = unit; pb < num_p_blocks && rank == 0; pb += num_units)
@@ -155,13 +162,13 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
                         const uint64_t da = make_desc_k_sw128(sa), db = make_desc_k_sw128(sa + S::kABytes);
 #pragma unroll
-                        for (int k = 0; k < ((a.debug & 2) ? 0 : 4); ++k) {   // one UMMA consumes 32 bytes of K (8 tf32 / 16 bf16) of the 128-byte row
+                        for (int k = 0; k < ((a.debug & 2) ? 0 : 4); ++k) {   // one UMMA consumes 32 bytes of K (8 tf32 / 16 fp16) of the 128-byte row
                             const uint64_t ak = da + (uint64_t)(2 * k), bk = db + (uint64_t)(2 * k);
                             if (CTAS == 1) {
-                                if (kBf16) umma_bf16(tmem_d, ak, bk, idesc, (kb | k) != 0);
+                                if (kHalf) umma_f16(tmem_d, ak, bk, idesc, (kb | k) != 0);
                                 else umma_tf32(tmem_d, ak, bk, idesc, (kb | k) != 0);
                             } else {
-                                if (kBf16) umma_bf16_pair(tmem_d, ak, bk, idesc, (kb | k) != 0);
+                                if (kHalf) umma_f16_pair(tmem_d, ak, bk, idesc, (kb | k) != 0);
                                 else umma_tf32_pair(tmem_d, ak, bk, idesc, (kb | k) != 0);
                             }
                         }
@@ -189,14 +196,26 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         constexpr uint32_t kIdxDelta = 2u * TC_BM * kCandStride * 4u;   // byte distance cand_s -> cand_i
         (void)my_i;
         constexpr int kChunksPerHalf = (BN / 32) / 2;
-        const float cmax = sqrtf(__uint_as_float(*a.cmax_bits));
+        const float cmax2 = __uint_as_float(a.cmax_bits[0]);
+        // tf32 operands: the hardware keeps 10 mantissa bits of each element, |dx_k| <= 2^-10 |x_k| whatever its rounding
+        const float dcmax2 = kHalf ? __uint_as_float(a.cmax_bits[1]) : cmax2 * 9.5367431640625e-7f;
+        const float cmax = sqrtf(cmax2), dcmax = sqrtf(dcmax2);
         int as = 0;
         uint32_t aphase = 0;
         for (int pb = unit; pb < num_p_blocks; pb += num_units) {
             const int mb = pb * CTAS + rank;
             const int64_t row = (int64_t)mb * TC_BM + row_in_tile;
             const bool valid = row < a.R;
-            const float band = valid ? a.beta * (kBf16 ? 3.90625e-3f : 9.765625e-4f) * sqrtf(a.xn[row]) * cmax : 0.0f;
+            // band = 4 e + fp32 slack of the re-check itself (its own rounding, and ties created by sqrt / clamp: two squared
+            // distances closer than 2^-21 (|x|^2 + |c|^2) can round to the same fp32 distance).  Non-finite rows give a NaN
+            // or infinite band: no candidate or every candidate is kept, and either way the row is rescanned exactly.
+            float band = 0.0f;
+            if (valid) {
+                const float xn2 = a.xn[row], xe2 = kHalf ? a.xe[row] : xn2 * 9.5367431640625e-7f;
+                const float nx = sqrtf(xn2), dx = sqrtf(xe2), nxh = nx + dx;
+                const float e = dx * cmax + nxh * dcmax + a.gamma * nxh * (cmax + dcmax);
+                band = 4.0f * e + 1.9073486328125e-6f * (xn2 + cmax2);
+            }
             float m_run = INFINITY;
             int cnt = 0;                  // candidates stored; kListSlots means "full: some may have been lost"
             for (int nb = 0; nb < a.num_n_blocks; ++nb) {
@@ -342,31 +361,43 @@ codebook_norms_kernel(const float *__restrict__ C, int M, int padded, int d, flo
     }
 }
 
-// fp32 rows -> bf16 copy (round to nearest even) + |row|^2 of the ORIGINAL fp32 row, one warp per row
+// fp32 rows -> fp16 copy (round to nearest even, saturated to the fp16 range), |row|^2 of the ORIGINAL fp32 row and the
+// squared norm of the rounding residual |row - fp16(row)|^2 (the measured quantity the candidate band is built from);
+// max_resid_bits (codebook): running maximum of the residuals' bit patterns.  One warp per row.
 __global__ void __launch_bounds__(256)
-rows_to_bf16_kernel(const float *__restrict__ x, int64_t rows, int d, unsigned short *__restrict__ xb, float *__restrict__ norm)
+rows_to_half_kernel(const float *__restrict__ x, int64_t rows, int d, unsigned short *__restrict__ xh, float *__restrict__ norm,
+                    float *__restrict__ resid, unsigned *max_resid_bits)
 {
     const int lane = threadIdx.x & 31;
     for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
         const float2 *p = reinterpret_cast<const float2 *>(x + r * d);
-        unsigned *q = reinterpret_cast<unsigned *>(xb + r * d);
-        float s = 0.0f;
+        unsigned *q = reinterpret_cast<unsigned *>(xh + r * d);
+        float s = 0.0f, e = 0.0f;
         for (int k = lane; k < d / 2; k += kWarp) {
             const float2 v = p[k];
             s = fmaf(v.x, v.x, s);
             s = fmaf(v.y, v.y, s);
-            const unsigned lo = __bfloat16_as_ushort(__float2bfloat16_rn(v.x)), hi = __bfloat16_as_ushort(__float2bfloat16_rn(v.y));
-            q[k] = lo | (hi << 16);
+            const __half h0 = __float2half_rn(fminf(fmaxf(v.x, -65504.0f), 65504.0f));
+            const __half h1 = __float2half_rn(fminf(fmaxf(v.y, -65504.0f), 65504.0f));
+            const float d0 = v.x - __half2float(h0), d1 = v.y - __half2float(h1);    // exact in fp32 (NaN / inf stay NaN / inf)
+            e = fmaf(d0, d0, e);
+            e = fmaf(d1, d1, e);
+            q[k] = (unsigned)__half_as_ushort(h0) | ((unsigned)__half_as_ushort(h1) << 16);
         }
         s = warp_sum(s);
-        if (lane == 0 && norm) norm[r] = s;
+        e = warp_sum(e) * 1.0000005f;          // the sum itself is rounded: keep the residual norm an upper bound
+        if (lane == 0) {
+            if (norm) norm[r] = s;
+            if (resid) resid[r] = e;
+            if (max_resid_bits) atomicMax(max_resid_bits, __float_as_uint(fabsf(e)));   // NaN bit patterns compare above +inf
+        }
     }
 }
 
-bool discretize_tc_supported(int64_t R, int d, int M, bool bf16)
+bool discretize_tc_supported(int64_t R, int d, int M, bool half)
 {
     // TMA needs 16-byte aligned row strides; tiny problems are not worth a tensor-core launch
-    return d % (bf16 ? 8 : 4) == 0 && d >= 32 && M >= 16 && R >= 1 && encode_tiled_fn() != nullptr;
+    return d % (half ? 8 : 4) == 0 && d >= 32 && M >= 16 && R >= 1 && encode_tiled_fn() != nullptr;
 }
 
 int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws, cudaStream_t st)
@@ -378,18 +409,18 @@ int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws,
     return 0;
 }
 
-template <int BN, bool kBf16, int CTAS>
+template <int BN, bool kHalf, int CTAS>
 static int launch_tc_n(const CUtensorMap &tmA, const CUtensorMap &tmB, const DiscTcArgs &a, cudaStream_t st)
 {
     using S = DiscTcSmem<BN, CTAS>;
     static bool configured = false;
     if (!configured) {
-        SH_CHECK_CUDA(cudaFuncSetAttribute(discretize_tc_kernel<BN, kBf16, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        SH_CHECK_CUDA(cudaFuncSetAttribute(discretize_tc_kernel<BN, kHalf, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         configured = true;
     }
     const int units = (a.num_m_blocks + CTAS - 1) / CTAS;
     const int num_units = min(units, sm_count() / CTAS);
-    const char *name = kBf16 ? "discretize_tc_bf16_kernel" : "discretize_tc_kernel";
+    const char *name = kHalf ? "discretize_tc_f16_kernel" : "discretize_tc_kernel";
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(num_units * CTAS);
     cfg.blockDim = dim3(TC_THREADS);
@@ -403,7 +434,7 @@ static int launch_tc_n(const CUtensorMap &tmA, const CUtensorMap &tmB, const Dis
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     prof_begin(name, st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, discretize_tc_kernel<BN, kBf16, CTAS>, tmA, tmB, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, discretize_tc_kernel<BN, kHalf, CTAS>, tmA, tmB, a);
     prof_end(st);
     if (e != cudaSuccess) { set_error("%s launch -> %s", name, cudaGetErrorString(e)); return 1; }
     SH_CHECK_LAUNCH();
@@ -417,15 +448,15 @@ static int disc_ctas()
     return c;
 }
 
-template <int BN, bool kBf16>
+template <int BN, bool kHalf>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const DiscTcArgs &a, cudaStream_t st)
 {
-    if (disc_ctas() == 2 && BN >= 128) return launch_tc_n<BN, kBf16, 2>(tmA, tmB, a, st);
-    return launch_tc_n<BN, kBf16, 1>(tmA, tmB, a, st);
+    if (disc_ctas() == 2 && BN >= 128) return launch_tc_n<BN, kHalf, 2>(tmA, tmB, a, st);
+    return launch_tc_n<BN, kHalf, 1>(tmA, tmB, a, st);
 }
 
-// bf16 row-major [rows, cols]: box {64 bf16 (128 B), box_rows}
-static int make_tmap_bf16(CUtensorMap *map, const unsigned short *base, uint64_t cols, uint64_t rows, uint32_t box_rows)
+// fp16 row-major [rows, cols]: box {64 halves (128 B), box_rows}
+static int make_tmap_f16(CUtensorMap *map, const unsigned short *base, uint64_t cols, uint64_t rows, uint32_t box_rows)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     SH_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available");
@@ -433,29 +464,29 @@ static int make_tmap_bf16(CUtensorMap *map, const unsigned short *base, uint64_t
     cuuint64_t strides[1] = {cols * 2};
     cuuint32_t box[2] = {64, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<unsigned short *>(base), dims, strides, box, estr,
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<unsigned short *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SH_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r);
+    SH_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d", (int)r);
     return 0;
 }
 
 int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M, int64_t *out_idx, int64_t idx_rows,
-                         int64_t idx_row_stride, int64_t idx_col_stride, const DiscWorkspace &ws, bool bf16, cudaStream_t st)
+                         int64_t idx_row_stride, int64_t idx_col_stride, const DiscWorkspace &ws, bool half, cudaStream_t st)
 {
     SH_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)C % 16 == 0), "discretize: tensor-core path needs 16-byte aligned inputs");
     const int BN = M > 128 ? 256 : (M > 64 ? 128 : 64);
     const int b_split = (disc_ctas() == 2 && BN >= 128) ? 2 : 1;   // CTA pairs stage half of the codebook tile each
     CUtensorMap tmA, tmB;
-    if (bf16) {
-        // one pass over the tokens produces the bf16 copy and |x|^2 (the fp32 path needs that pass for |x|^2 anyway)
+    if (half) {
+        // one pass over the tokens produces the fp16 copy, |x|^2 and the residual norms (the fp32 path needs a pass for |x|^2 anyway)
         const int g1 = (int)min(ceil_div64(R, 8), (int64_t)sm_count() * 16), g2 = (int)min(ceil_div64(M, 8), (int64_t)sm_count() * 16);
-        SH_LAUNCH("rows_to_bf16_kernel", st, rows_to_bf16_kernel<<<g1, 256, 0, st>>>(X, R, d, ws.xb, ws.xn));
+        SH_LAUNCH("rows_to_half_kernel", st, rows_to_half_kernel<<<g1, 256, 0, st>>>(X, R, d, ws.xb, ws.xn, ws.xe, nullptr));
         SH_CHECK_LAUNCH();
-        SH_LAUNCH("rows_to_bf16_kernel", st, rows_to_bf16_kernel<<<g2, 256, 0, st>>>(C, M, d, ws.cb, nullptr));
+        SH_LAUNCH("rows_to_half_kernel", st, rows_to_half_kernel<<<g2, 256, 0, st>>>(C, M, d, ws.cb, nullptr, nullptr, (unsigned *)(ws.counters + 2) + 1));
         SH_CHECK_LAUNCH();
-        if (make_tmap_bf16(&tmA, ws.xb, (uint64_t)d, (uint64_t)R, TC_BM)) return 1;
-        if (make_tmap_bf16(&tmB, ws.cb, (uint64_t)d, (uint64_t)M, (uint32_t)(BN / b_split))) return 1;
+        if (make_tmap_f16(&tmA, ws.xb, (uint64_t)d, (uint64_t)R, TC_BM)) return 1;
+        if (make_tmap_f16(&tmB, ws.cb, (uint64_t)d, (uint64_t)M, (uint32_t)(BN / b_split))) return 1;
     } else {
         if (make_tmap_f32(&tmA, X, (uint64_t)d, (uint64_t)R, 1, (uint64_t)d, 0, TC_BM)) return 1;
         if (make_tmap_f32(&tmB, C, (uint64_t)d, (uint64_t)M, 1, (uint64_t)d, 0, (uint32_t)(BN / b_split))) return 1;
@@ -465,17 +496,18 @@ int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M
     a.R = R; a.d = d; a.M = M;
     a.num_m_blocks = (int)ceil_div64(R, TC_BM);
     a.num_n_blocks = ceil_div(M, BN);
-    a.num_k_blocks = ceil_div(d, bf16 ? 64 : TC_BK);
+    a.num_k_blocks = ceil_div(d, half ? 64 : TC_BK);
     a.cn = ws.cn; a.xn = ws.xn; a.cmax_bits = (const unsigned *)(ws.counters + 2);
-    // band = beta * 2^-10 * |x| * max|c|: >= 13 sigma of the tf32 truncation noise for i.i.d. data, and the rigorous
-    // worst-case bound when beta reaches 8 ("tf32 band")
-    float beta = 16.0f / sqrtf((float)d);
-    a.beta = beta < 1.0f ? 1.0f : (beta > 8.0f ? 8.0f : beta);
+    a.xe = ws.xe;
+    // fp32 accumulation of d exact products, in whatever order and with truncating adds (unit roundoff 2^-23): the error
+    // is at most (d - 1) 2^-23 sum_k |x^_k c^_k| <= d 2^-23 |x^| |c^| (Higham, Accuracy and Stability, 4.2); doubled as a
+    // margin for the alignment shifts inside one UMMA k-step
+    a.gamma = 2.0f * (float)d * 1.1920928955078125e-7f;
     a.out_idx = out_idx; a.idx_rows = idx_rows; a.idx_row_stride = idx_row_stride; a.idx_col_stride = idx_col_stride;
     a.cand_count = ws.cand_count; a.cand_idx = ws.cand_idx;
     { const char *e = getenv("SCHEMANET_DISC_DEBUG"); a.debug = e ? atoi(e) : 0; }
     int rc;
-    if (bf16) {
+    if (half) {
         if (BN == 256) rc = launch_tc<256, true>(tmA, tmB, a, st);
         else if (BN == 128) rc = launch_tc<128, true>(tmA, tmB, a, st);
         else rc = launch_tc<64, true>(tmA, tmB, a, st);

@@ -15,7 +15,7 @@ ABI_VERSION = 1
 
 NO_CLAMP = -3.0e38
 G_RAW_LOGITS, G_FROM_HEADS, G_SUM, G_WRITE_BACK_CLAMP, G_ZERO_PAD = 1, 2, 4, 8, 16
-DISC_AUTO, DISC_EXACT, DISC_TENSOR, DISC_TENSOR_BF16 = 0, 1, 2, 3
+DISC_AUTO, DISC_EXACT, DISC_TENSOR, DISC_TENSOR_F16 = 0, 1, 2, 3
 SIM_KINDS = {"inner_product": 0, "cosine": 1, "euclidean": 2}
 
 # every symbol include/schemahead.h declares (tests/test_abi.py checks the header against this list and the .so)

@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Times stage 1 alone (CUDA events, L2 flushed between iterations) for one or more shapes.
-usage: tools/disc_bench.py [B d M mode]...   mode in {auto, exact, tf32, bf16}"""
+usage: tools/disc_bench.py [B d M mode]...   mode in {auto, exact, tf32, f16}"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "schemanet-pytorch_b200"))
 import torch
 from schemanet_b200 import native
 
-MODES = {"auto": native.DISC_AUTO, "exact": native.DISC_EXACT, "tf32": native.DISC_TENSOR, "bf16": native.DISC_TENSOR_BF16}
+MODES = {"auto": native.DISC_AUTO, "exact": native.DISC_EXACT, "tf32": native.DISC_TENSOR, "f16": native.DISC_TENSOR_F16}
 args = sys.argv[1:] or ["256", "384", "1024", "auto"]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for i in range(0, len(args), 4):

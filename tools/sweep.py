@@ -25,8 +25,8 @@ Ms = [256, 1024, 8192] if args.quick else [256, 512, 1024, 2048, 4096, 8192]
 Bs = [1, 64, 1024] if args.quick else [1, 4, 16, 64, 256, 1024, 4096]
 d, K, Vc, D, L = 384, 100, 256, 256, 196
 dev = torch.device("cuda")
-STAGES = {"discretize": ("rows_to_bf16_kernel", "codebook_norms_kernel", "row_sqnorm_kernel", "discretize_tc_kernel",
-                         "discretize_tc_bf16_kernel", "discretize_exact_kernel", "discretize_recheck_kernel"),
+STAGES = {"discretize": ("rows_to_half_kernel", "codebook_norms_kernel", "row_sqnorm_kernel", "discretize_tc_kernel",
+                         "discretize_tc_f16_kernel", "discretize_exact_kernel", "discretize_recheck_kernel"),
           "graph": ("instance_graph_kernel",),
           "match": ("gnn_adj_prep", "gnn_embed_gather", "gnn_embed_table_linear", "gnn_split_weights", "gnn_adj_gemm_tc",
                     "gnn_adj_ln_tc", "gnn_linear_ln_tc", "gnn_linear_tc", "gnn_ln_relu_wide", "gnn_pool_rows", "gnn_pool_fc",
