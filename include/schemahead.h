@@ -133,6 +133,13 @@ int sh_dev_feat_to_v_attr(const int64_t *ingredients, const float *attn_cls, int
 int sh_dev_feat_to_e(const int64_t *ingredients, const float *attn, const float *geo_sim,
                      const int64_t *class_ingredients, const int64_t *label, int B, int L, int K, int n_max, int mean,
                      float *out, sh_stream_t stream);
+/* Per-class running sums of the atlas initialisation: replaces the Python accumulation loops of
+ * scripts/init_schema_net.py:31-34 (edges) and :57-59 (vertices),
+ *     for cls_id, x_b in zip(label, x): acc[cls_id] += x_b; n_tracked[cls_id] += 1
+ *   x [B, N] fp32 (one flattened sample per row), label [B] int64, acc [K, N] fp32 and n_tracked [K] fp32 (or NULL) are
+ *   updated in place; samples are added in batch order (the reference's fp32 summation order: bit-exact). */
+int sh_dev_class_accumulate(const float *x, const int64_t *label, int B, int64_t N, int K, float *acc, float *n_tracked,
+                            sh_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Stage 3a -- class IR-atlas.

@@ -141,6 +141,111 @@ def run_init_case(ns, name, B, M, K, Vc, seed):
     print(f"{name}: B={B} M={M} K={K} Vc={Vc}")
 
 
+def run_init_callers_case(ns, name, nb, B, M, K, Vc, seed):
+    """Atlas initialisation as scripts/init_schema_net.py:19-65,108-124 runs it: the reference's own init_class_vertices /
+    init_graph (imported unmodified; the DataLoader and the backbone wrapper are stand-ins that replay fixed batches)
+    over the reference SchemaNet.feat_to_full_vertices / feat_to_limited_edges (schema_net.py:188-274)."""
+    import importlib
+    init_mod = importlib.import_module("scripts.init_schema_net")
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)                      # SchemaNet._reset_parameters draws the initial edge_weights
+    sn = ns.SchemaNet(M, K, class_max_vertices=Vc, **{k: v for k, v in ho.HEAD_CFG.items() if k != "num_layers"})
+    sn.vertex_attribute_weights.copy_(torch.tensor([[0.25], [1.5]]))
+    sn.edge_attribute_weights.copy_(torch.tensor([[2.0], [0.125]]))
+    batches = []
+    for i in range(nb):
+        label = torch.randint(0, K, (B,), generator=g)
+        label[:K] = torch.randperm(K, generator=g)           # every class is seen (n_tracked > 0)
+        batches.append(dict(ingredients=torch.randint(0, M, (B, L), generator=g),
+                            attn=0.5 * torch.randn(B, L, L, generator=g), attn_cls=0.5 * torch.randn(B, L, generator=g),
+                            label=label))
+    out = dict(cfg=np.array([nb, B, M, K, Vc], dtype=np.int64), w_v=sn.vertex_attribute_weights.tensor.detach().numpy().copy(),
+               w_e=sn.edge_attribute_weights.tensor.detach().numpy().copy())
+    for i, b in enumerate(batches):
+        for k, v in b.items():
+            out[f"batch{i}.{k}"] = v.numpy().copy()
+    loader = [(torch.tensor([i]), {"label": b["label"]}) for i, b in enumerate(batches)]
+
+    def wrapper(x):                              # the reference methods clamp their inputs in place -> hand out copies
+        b = batches[int(x[0])]
+        return {k: v.clone() for k, v in b.items() if k != "label"}
+
+    dev = torch.device("cpu")
+    with torch.no_grad():
+        out["full_vertices0"] = sn.feat_to_full_vertices(batches[0]["ingredients"], batches[0]["attn_cls"].clone()).numpy().copy()
+        cv = init_mod.init_class_vertices(loader, wrapper, graph=sn, device=dev)
+        out["class_vertices_full"] = cv.numpy().copy()
+        init_w, valid = cv.topk(Vc, dim=1)
+        sn.register_class_vertices(valid)
+        sn.vertex_weights.copy_(init_w)
+        out["valid_vertices"], out["vertex_weights"] = valid.numpy().copy(), init_w.numpy().copy()
+        out["edge_weights_init"] = sn.edge_weights.tensor.detach().numpy().copy()
+        out["limited_edges0"] = sn.feat_to_limited_edges(batches[0]["ingredients"], batches[0]["attn"].clone(),
+                                                         batches[0]["label"]).numpy().copy()
+        init_mod.init_graph(loader, wrapper, graph=sn, device=dev)
+        out["edge_weights_final"] = sn.edge_weights.tensor.detach().numpy().copy()
+        out["vertex_weights_final"] = sn.vertex_weights.tensor.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: nb={nb} B={B} M={M} K={K} Vc={Vc}")
+
+
+def run_train_case(ns, name, B, d, M, K, Vc, D, seed):
+    """One training iteration of the head as SchemaNetTrainer.train_iter runs it (tasks/worker_schema_net.py:120-140):
+    normalize(), forward (SchemaNet.forward, get_atlas, Matcher.forward in grad mode), SchemaInferenceLoss
+    (loss/schema_inference_loss.py:21-47) with the shipped weights (config/*/schema_net/*.yaml: cls 1, re_entropy_vertex 0.5,
+    re_entropy_edge 0.75), backward.  Stores the loss terms and the gradient of every parameter."""
+    from schema_inference.loss.schema_inference_loss import SchemaInferenceLoss
+    vocab, mid, attn, attn_cls = ho.synth_inputs(B, d, M, seed, L, "easy")
+    schema = ho.synth_schema(M, K, Vc, seed + 1)
+    schema["w_v"] = torch.tensor([[0.25], [1.5]])
+    schema["w_e"] = torch.tensor([[2.0], [0.125]])
+    schema["vertex_weights"][:, 2::5] = 0.0                    # pruned vertices (normalised weight 1e-5 / sum <= 0.001)
+    schema["vertex_weights"][1, :3] = 0.0
+    gnn = ho.synth_gnn(M, D, seed + 2)
+    g = torch.Generator().manual_seed(seed + 3)
+    gnn["layers.0.norm.weight"] = torch.rand(D, generator=g) + 0.5
+    gnn["layers.1.norm.bias"] = 0.1 * torch.randn(D, generator=g)
+    gnn["fc.bias"] = 0.1 * torch.randn(D, generator=g)
+    label = torch.randint(0, K, (B,), generator=g)
+    disc, sn, matcher = load_params(ns, M, d, K, Vc, D, vocab, schema, gnn)
+    out = dict(vocab=vocab.numpy(), mid_feat=mid.numpy(), attn=attn.numpy(), attn_cls=attn_cls.numpy(), label=label.numpy(),
+               cfg=np.array([B, d, M, K, Vc, D], dtype=np.int64))
+    for k, v in schema.items():
+        out["schema." + k] = v.numpy()
+    for k, v in gnn.items():
+        out["gnn." + k] = v.numpy()
+    with torch.no_grad():
+        ad = ns.Adapter()
+        _, match = disc(ad.adapt(mid))
+        ingredients = match.t().contiguous()
+    out["ingredients"] = ingredients.numpy()
+    sn.train(); matcher.train()
+    sn.normalize()
+    for k, v in sn.state_dict().items():
+        out["after_normalize." + k] = v.numpy().copy()
+    inst = sn(ingredients, attn.clone(), attn_cls.clone())
+    atlas = sn.get_atlas()
+    out["pruned_entries"] = np.array([(torch.from_numpy(out["after_normalize.edge_weights.tensor"]) != sn.edge_weights.tensor).sum().item()],
+                                     dtype=np.int64)
+    pred = matcher(inst, atlas)
+    loss_fn = SchemaInferenceLoss(re_a_vertex=3.0, re_a_edge=4.0)
+    terms = loss_fn({"pred": pred, **atlas}, {"label": label})
+    weights = {"cls": 1.0, "re_entropy_vertex": 0.5, "re_entropy_edge": 0.75}
+    total = sum(terms[k] * w for k, w in weights.items())
+    total.backward()
+    out["pred"] = pred.detach().numpy()
+    out["loss_total"] = np.array([total.item()], dtype=np.float64)
+    for k, v in terms.items():
+        out["loss." + k] = np.array([v.item()], dtype=np.float64)
+    for prefix, mod in (("grad.schema_net.", sn), ("grad.matcher.", matcher)):
+        for k, p_ in mod.named_parameters():
+            if p_.requires_grad:
+                out[prefix + k] = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).numpy().copy()
+    out["after_step.edge_weights.tensor"] = sn.edge_weights.tensor.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: pruned {out['pruned_entries'][0]} loss {total.item():.6f} terms { {k: round(v.item(), 5) for k, v in terms.items()} }")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)          # fixtures must not depend on the thread count of the generating host
@@ -150,6 +255,8 @@ def main():
                   edit=edit_edge_cases, w_v=[0.25, 1.5], w_e=[2.0, 0.125])
     run_head_case(ns, "head_wide", B=2, d=192, M=1024, K=3, Vc=64, D=256, seed=303, mode="easy")
     run_init_case(ns, "init_apis", B=3, M=64, K=4, Vc=24, seed=404)
+    run_init_callers_case(ns, "init_callers", nb=2, B=5, M=48, K=3, Vc=16, seed=505)
+    run_train_case(ns, "train_step", B=3, d=32, M=40, K=3, Vc=24, D=32, seed=606)
 
 
 if __name__ == "__main__":

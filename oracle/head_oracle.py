@@ -294,6 +294,139 @@ def head_forward(mid_feat, attn, attn_cls, vocab, schema, gnn_params, cfg, ext=N
 
 
 # --------------------------------------------------------------------------------------------------------------
+# atlas initialisation  (schema_net.py:188-274, scripts/init_schema_net.py:19-65)
+# --------------------------------------------------------------------------------------------------------------
+def feat_to_full_vertices(ingredients, attn_cls, num_vertices, w_v, clamp_vertex=None):
+    """SchemaNet.feat_to_full_vertices (schema_net.py:188-207) -> [bs, M].  Works on a copy of attn_cls."""
+    attn_cls = attn_cls.clone()
+    if clamp_vertex is not None:
+        attn_cls.masked_fill_(attn_cls < clamp_vertex, float("-inf"))
+    attrs = feat_to_v_attr(ingredients, attn_cls.softmax(dim=-1), num_vertices, mean=True)          # :202
+    attrs = (attrs / attrs.max(dim=1, keepdim=True)[0]).nan_to_num(0)                                # normalize_max_, :204
+    return (attrs @ w_v.reshape(2, 1)).squeeze(-1)
+
+
+def feat_to_limited_edges(ingredients, attn, class_ingredients, label, w_e, clamp_edge=None, remove_self_loop=False,
+                          feat_h=14, feat_w=14, dist_alpha=1.0, dist_pow=2.0):
+    """SchemaNet.feat_to_limited_edges (schema_net.py:222-254) -> [bs, Vc, Vc].  Works on a copy of attn."""
+    attn = attn.clone()
+    if clamp_edge is not None:
+        attn.masked_fill_(attn < clamp_edge, float("-inf"))
+    geo = pair_wise_point_sim(feat_h, feat_w, dist_alpha, dist_pow)
+    attrs = feat_to_e(ingredients, torch.softmax(attn, dim=-1), geo, class_ingredients, label, class_ingredients.shape[1], True)
+    attrs = (attrs / attrs.sum(dim=2, keepdim=True)).nan_to_num(0)                                   # normalize_sum_, :248
+    if remove_self_loop:
+        attrs.diagonal(dim1=1, dim2=2).fill_(0)
+    return (attrs @ w_e.reshape(2, 1)).squeeze(-1)
+
+
+def init_class_vertices(batches, num_classes, num_vertices, w_v, clamp_vertex=None):
+    """scripts/init_schema_net.py:43-65: per-class mean of the full vertex weights, rows normalised to sum 1."""
+    acc = torch.zeros(num_classes, num_vertices)
+    n_tracked = torch.zeros(num_classes)
+    for b in batches:
+        v = feat_to_full_vertices(b["ingredients"], b["attn_cls"], num_vertices, w_v, clamp_vertex)
+        for cls_id, inst in zip(b["label"].tolist(), v):                                             # :57-59, in order
+            acc[cls_id] += inst
+            n_tracked[cls_id] += 1
+    acc /= n_tracked[:, None]
+    acc /= acc.sum(dim=-1, keepdim=True)
+    return acc
+
+
+def init_graph(batches, edge_weights, class_ingredients, w_e, clamp_edge=None, remove_self_loop=False):
+    """scripts/init_schema_net.py:19-40 up to (not including) graph.normalize(): edge_weights (modified in place) += the
+    class-local edges of every sample, then / n_tracked."""
+    n_tracked = torch.zeros(edge_weights.shape[0])
+    for b in batches:
+        e = feat_to_limited_edges(b["ingredients"], b["attn"], class_ingredients, b["label"], w_e, clamp_edge, remove_self_loop)
+        for cls_id, inst in zip(b["label"].tolist(), e):                                             # :32-34
+            edge_weights[cls_id] += inst
+            n_tracked[cls_id] += 1
+    edge_weights /= n_tracked[:, None, None]
+    return edge_weights
+
+
+def schema_normalize(schema, apply_normalize=True, clamp_weights=True, remove_self_loop=False):
+    """SchemaNet.normalize (schema_net.py:131-142), in place on the dict's tensors."""
+    with torch.no_grad():
+        if clamp_weights:
+            schema["w_v"].clamp_(min=0.01, max=10)
+            schema["w_e"].clamp_(min=0.01, max=10)
+        if apply_normalize:
+            for k in ("vertex_weights", "edge_weights"):
+                x = schema[k].clamp_min_(0)
+                x /= x.sum(dim=-1, keepdim=True)
+                x.nan_to_num_(0)
+            if remove_self_loop:
+                schema["edge_weights"].diagonal(dim1=1, dim2=2).fill_(0)
+    return schema
+
+
+# --------------------------------------------------------------------------------------------------------------
+# training step  (tasks/worker_schema_net.py:120-140, loss/schema_inference_loss.py:21-67)
+# --------------------------------------------------------------------------------------------------------------
+def class_atlas_train(vertex_weights, edge_weights, class_ingredients, prune_node_threshold=None, remove_self_loop=False):
+    """get_atlas in grad mode: the row sums are DETACHED (normalize_sum_clamp(detach_sum=True), schema_net.py:149,168), the
+    pruned entries are zeroed in place under no_grad and masked again so that their gradient is zero (:157-166)."""
+    def nsc(x, min_val=0.0):
+        x = x.clamp_min(min_val)
+        return (x / x.sum(dim=-1, keepdim=True).detach()).nan_to_num(0)
+    cv = nsc(vertex_weights, 1.0e-5)
+    ew = edge_weights
+    if prune_node_threshold is not None:
+        with torch.no_grad():
+            mask = (nsc(vertex_weights.detach(), 1.0e-5) > prune_node_threshold).float().unsqueeze(-1)
+            mask = torch.bmm(mask, mask.transpose(1, 2))
+            edge_weights.masked_fill_(~mask.bool(), 0)
+        ew = edge_weights * mask
+    ce = nsc(ew)
+    if remove_self_loop:
+        m = torch.ones_like(ce)
+        m.diagonal(dim1=1, dim2=2).fill_(0)
+        ce = ce * m
+    return {"class_vertices": cv, "class_edges": ce, "class_ingredients": class_ingredients}
+
+
+def entropy(p, eps=1.0e-7):
+    return -torch.sum(p * torch.log(p + eps), dim=-1)                                                # loss :50-57
+
+
+def rectify_linear(x, a=0.0):
+    return x if x > a else a - 1 + 1.0 / (1 + a - x)                                                  # loss :60-67
+
+
+def schema_inference_loss(pred, class_vertices, class_edges, label, re_a_vertex=3.0, re_a_edge=3.0):
+    """SchemaInferenceLoss.forward (loss/schema_inference_loss.py:21-47)."""
+    ev = entropy(class_vertices).max(dim=0)[0]
+    ee = entropy(class_edges).max(dim=1)[0].mean()
+    return {"cls": F.cross_entropy(pred, label), "entropy_vertex": ev, "entropy_edge": ee,
+            "re_entropy_vertex": rectify_linear(ev, re_a_vertex), "re_entropy_edge": rectify_linear(ee, re_a_edge)}
+
+
+def train_forward(ingredients, attn, attn_cls, schema, gnn_params, cfg):
+    """The head's forward in grad mode on leaf tensors that require grad (schema: vertex_weights, edge_weights, w_v, w_e;
+    gnn_params).  The 2 -> 1 attribute mixes stay in torch so that autograd reaches w_v / w_e, like the reference's trailing
+    matmul (large_scale_feat_to_v.cpp:124-125, large_scale_feat_to_e.cpp:135-140)."""
+    e0, e1 = torch.tensor([1.0, 0.0]), torch.tensor([0.0, 1.0])
+    g0 = instance_graphs(ingredients, attn, attn_cls, e0, e0, cfg.get("clamp_vertex_attn"), cfg.get("clamp_edge_attn"))
+    g1 = instance_graphs(ingredients, attn, attn_cls, e1, e1, cfg.get("clamp_vertex_attn"), cfg.get("clamp_edge_attn"))
+    wv, we = schema["w_v"].reshape(-1), schema["w_e"].reshape(-1)
+    inst = {"instance_ingredients": g0["instance_ingredients"],
+            "instance_vertices": [a * wv[0] + b * wv[1] for a, b in zip(g0["instance_vertices"], g1["instance_vertices"])],
+            "instance_edges": [a * we[0] + b * we[1] for a, b in zip(g0["instance_edges"], g1["instance_edges"])]}
+    atlas = class_atlas_train(schema["vertex_weights"], schema["edge_weights"], schema["class_ingredients"],
+                              cfg.get("prune_node_threshold"), cfg.get("remove_self_loop", False))
+    # match() pads with plain tensor assignment, which keeps the graph
+    pid, pw, pe, mask = pad_instance_graphs(inst, gnn_params["embedding.weight"].shape[0] - 1)
+    f_inst = gnn_forward(gnn_params, pw, pe, pid, mask, cfg.get("num_layers", 2))
+    f_kg = gnn_forward(gnn_params, atlas["class_vertices"], atlas["class_edges"], atlas["class_ingredients"], None,
+                       cfg.get("num_layers", 2))
+    pred = (f_inst.unsqueeze(1) * f_kg.unsqueeze(0)).sum(-1)
+    return pred, atlas
+
+
+# --------------------------------------------------------------------------------------------------------------
 # seeded synthetic inputs (SURVEY.md section 8d) -- shared by gen_golden.py, the tests and bench.py
 # --------------------------------------------------------------------------------------------------------------
 CONFIGS = {

@@ -789,6 +789,41 @@ extern "C" int sh_dev_instance_graphs(const int64_t *ingredients, float *attn, f
     return 0;
 }
 
+// Per-class running sums of the atlas initialisation (scripts/init_schema_net.py:31-34, 57-59):
+//     for cls_id, x_b in zip(label, x): acc[cls_id] += x_b;  n_tracked[cls_id] += 1
+// One thread per element of a sample (N elements, coalesced), the batch walked IN ORDER, so every accumulator sees the
+// reference's sequential fp32 additions (bit-exact) and no atomics are needed.  Labels outside [0, K) are skipped.
+namespace sh {
+__global__ void __launch_bounds__(256)
+class_accumulate_kernel(const float *__restrict__ x, const int64_t *__restrict__ label, int B, int64_t N, int K,
+                        float *__restrict__ acc, float *__restrict__ n_tracked)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < N)
+        for (int b = 0; b < B; ++b) {
+            const int64_t k = label[b];
+            if (k >= 0 && k < K) acc[k * N + e] += x[(int64_t)b * N + e];
+        }
+    if (e == 0 && n_tracked)
+        for (int b = 0; b < B; ++b) {
+            const int64_t k = label[b];
+            if (k >= 0 && k < K) n_tracked[k] += 1.0f;
+        }
+}
+}  // namespace sh
+
+extern "C" int sh_dev_class_accumulate(const float *x, const int64_t *label, int B, int64_t N, int K, float *acc,
+                                       float *n_tracked, sh_stream_t stream)
+{
+    SH_REQUIRE(B > 0 && N > 0 && K > 0, "class_accumulate: bad shape B=%d N=%lld K=%d", B, (long long)N, K);
+    const int64_t grid = ceil_div64(N, 256);
+    SH_REQUIRE(grid < 2147483647LL, "class_accumulate: sample too large");
+    SH_LAUNCH("class_accumulate_kernel", (cudaStream_t)stream,
+              sh::class_accumulate_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(x, label, B, N, K, acc, n_tracked));
+    SH_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int sh_dev_feat_to_v_attr(const int64_t *ingredients, const float *attn_cls, int B, int L, int n_vertices,
                                      int mean, int ingredients_only, float *out, sh_stream_t stream)
 {

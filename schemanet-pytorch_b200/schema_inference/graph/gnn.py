@@ -4,7 +4,8 @@ reference's parameter names (`embedding.weight`, `layers.{i}.g_conv.linear.*`, `
 `GNN.forward` runs in libschemahead (`sh_dev_gnn_forward`): the symmetrised adjacency (E + E^T)/2 + I is formed while
 tiles are staged (the reference materialises three [bs, n, n] temporaries per layer), the embedding gather is fused
 into the first product, bias into the GEMM epilogue, LayerNorm + ReLU (+ the weighted mean pooling on the last layer)
-into one pass.  Inference only: there is no backward for these kernels yet.
+into one pass.  Training: `GNN.forward` in grad mode goes through `autograd.GnnFn` (kernels forward, recompute-and-differentiate
+backward); the fused packed / class-side entry points stay forward-only.
 """
 import torch
 import torch.nn as nn
@@ -70,16 +71,17 @@ class GNN(nn.Module):
             self._pack_key = key
         return self._pack
 
-    def _check_inference(self):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("schemanet_b200: the GNN backward pass is not built yet (SURVEY.md section 8 f3); "
-                                      "call under torch.no_grad()")
+    def _grad_mode(self, *inputs) -> bool:
+        return torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                            any(t is not None and t.requires_grad for t in inputs))
 
-    def forward(self, nodes: torch.Tensor, edges: torch.Tensor, ingredients: torch.LongTensor,
-                feat_mask: torch.BoolTensor = None):
-        """nodes [bs, n] vertex weights, edges [bs, n, n], ingredients [bs, n] code ids (num_codes = padding),
-        feat_mask [bs, n] True at padded TRAILING nodes -> graph embedding [bs, embed_dim]."""
-        self._check_inference()
+    def _check_inference(self):
+        """The packed / fused kernel entry points have no backward; training goes through `forward` (GnnFn)."""
+        if self._grad_mode():
+            raise NotImplementedError("schemanet_b200: this fused entry point is forward-only; in grad mode call GNN.forward "
+                                      "(autograd through schema_inference.graph.autograd.GnnFn) or wrap the call in torch.no_grad()")
+
+    def _forward_kernels(self, nodes, edges, ingredients, feat_mask):
         bs, n = nodes.shape
         sizes = None
         if feat_mask is not None:
@@ -87,12 +89,26 @@ class GNN(nn.Module):
         edges = edges if edges.is_contiguous() else edges.contiguous()
         nodes = nodes if nodes.is_contiguous() else nodes.contiguous()
         ingredients = ingredients if ingredients.is_contiguous() else ingredients.contiguous()
-        return native.gnn_forward(self.param_pack(), bs, n, sizes, ingredients, nodes.detach(), n, edges.detach(),
-                                  n * n, n, None, ws_key=("gnn", n >= 256))
+        return native.gnn_forward(self.param_pack(), bs, n, sizes, ingredients, nodes, n, edges, n * n, n, None,
+                                  ws_key=("gnn", n >= 256))
+
+    def forward(self, nodes: torch.Tensor, edges: torch.Tensor, ingredients: torch.LongTensor,
+                feat_mask: torch.BoolTensor = None):
+        """nodes [bs, n] vertex weights, edges [bs, n, n], ingredients [bs, n] code ids (num_codes = padding),
+        feat_mask [bs, n] True at padded TRAILING nodes -> graph embedding [bs, embed_dim].
+        In grad mode the result carries autograd history to nodes, edges and every parameter (gnn.py:78-98)."""
+        if self._grad_mode(nodes, edges):
+            from .autograd import GnnFn
+            L = self.layers
+            params = [self.embedding.weight, self.fc.weight, self.fc.bias] + [l.g_conv.linear.weight for l in L] + \
+                     [l.g_conv.linear.bias for l in L] + [l.norm.weight for l in L] + [l.norm.bias for l in L]
+            self.param_pack()                         # (raises for configurations the kernels do not implement)
+            return GnnFn.apply(self, feat_mask, ingredients, nodes, edges, *params)
+        return self._forward_kernels(nodes.detach(), edges.detach(), ingredients, feat_mask)
 
     def forward_packed(self, g: "native.PackedGraphs"):
         """Instance graphs straight from stage 2's packed slots: no padding, no host synchronisation; the mean
-        divisor (the padded length N = max_b n_b, gnn.py:96) is read on the device."""
+        divisor (the padded length N = max_b n_b, gnn.py:96) is read on the device.  Forward-only."""
         self._check_inference()
         L = g.L
         return native.gnn_forward(self.param_pack(), g.B, L, g.num_vertices, g.ids, g.vertex_w, L, g.edges, L * L, L,

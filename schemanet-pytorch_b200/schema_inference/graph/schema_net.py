@@ -65,6 +65,8 @@ class SchemaNet(nn.Module):
             setattr(self, name, cfg[name])
         # the reference also writes -inf into the caller's attention tensors (schema_net.py:296,335); kept by default
         self.write_back_clamp = True
+        # training: the reference's autograd gives fully pruned edge rows NaN gradients (0/0 behind nan_to_num); kept by default
+        self.nan_grad_on_pruned_rows = True
 
         self.register_buffer("n_tracked", torch.zeros(num_classes), persistent=False)
         if class_max_vertices is None:
@@ -125,20 +127,24 @@ class SchemaNet(nn.Module):
 
     def get_class_vertices(self, detach: bool = False) -> torch.Tensor:
         if not detach and self._grad_mode():
-            raise NotImplementedError("schemanet_b200: the atlas backward pass is not built yet (SURVEY.md section 8 f3); "
-                                      "call under torch.no_grad() or with detach=True")
+            from .autograd import ClassVerticesFn
+            return ClassVerticesFn.apply(self.vertex_weights.tensor)
         return self._atlas(False)[0]
 
     def get_class_edges(self, detach: bool = False) -> torch.Tensor:
         if not detach and self._grad_mode():
-            raise NotImplementedError("schemanet_b200: the atlas backward pass is not built yet (SURVEY.md section 8 f3); "
-                                      "call under torch.no_grad() or with detach=True")
+            from .autograd import ClassEdgesFn
+            return ClassEdgesFn.apply(self.edge_weights.tensor, self.vertex_weights.tensor.detach(), self.prune_node_threshold,
+                                      self.remove_self_loop, self.nan_grad_on_pruned_rows)
         return self._atlas(True)[1]
 
     def get_atlas(self, detach: bool = False) -> Dict[str, torch.Tensor]:
         if not detach and self._grad_mode():
-            raise NotImplementedError("schemanet_b200: the atlas backward pass is not built yet (SURVEY.md section 8 f3); "
-                                      "call under torch.no_grad() or with detach=True")
+            # training (worker_schema_net.py:129-139): the atlas tensors carry autograd history to the two parameters
+            atlas = Atlas(class_vertices=self.get_class_vertices(), class_edges=self.get_class_edges(),
+                          class_ingredients=self.class_ingredients.tensor)
+            atlas.prune_node_threshold = self.prune_node_threshold
+            return atlas
         class_vertices, class_edges = self._atlas(True)
         atlas = Atlas(class_vertices=class_vertices, class_edges=class_edges,
                       class_ingredients=self.class_ingredients.tensor)
@@ -175,6 +181,8 @@ class SchemaNet(nn.Module):
         assert len(self.class_ingredient_dict) > 0, "run `register_class_vertices` before"
         dev = ingredients.device
         ci = self.class_ingredients.tensor.to(dev)
+        if label.numel() and (int(label.min()) < 0 or int(label.max()) >= self.num_classes):
+            raise IndexError(f"label out of range [0, {self.num_classes})")      # (the kernels index class rows unchecked)
         if ingredients.is_cuda:
             return native.feat_to_e(ingredients, attn, geo_sim, ci, label.to(dev), self.class_max_vertices, True)
         return native.host_feat_to_e(ingredients, attn, geo_sim, ci, label, self.class_max_vertices, True)
@@ -185,6 +193,10 @@ class SchemaNet(nn.Module):
                                             self.edge_attribute_weights.tensor.requires_grad)
 
     def _build(self, ingredients, attn, attn_cls, want_vertices=True, want_edges=True, w_v=None, w_e=None) -> "native.PackedGraphs":
+        if want_edges and self.remove_self_loop:
+            # the reference cannot build instance edges with this flag: `instance_edges.diagonal(0, 1)` asks for
+            # dim1 == dim2 and throws (cpp_extension/src/large_scale_feat_to_e.cpp:136-139); same error here
+            raise RuntimeError("diagonal dimensions cannot be identical 1, 1")
         dev = ingredients.device
         return native.instance_graphs(
             ingredients, attn, attn_cls, self._geo(dev) if want_edges else None,

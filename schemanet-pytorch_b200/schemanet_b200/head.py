@@ -58,6 +58,8 @@ class SchemaHead:
         self._class_out = None
         self._fork = None
         self._join = None
+        self._shard_out = None
+        self._shard_ce = None
 
     # -- stage 1 -------------------------------------------------------------------------------------------------
     def discretize(self, mid_feat: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
@@ -100,14 +102,21 @@ class SchemaHead:
         per = (K + world - 1) // world
         k0, k1 = min(rank * per, K), min((rank + 1) * per, K)
         D = gnn.embed_dim
-        local = torch.zeros(per, D, dtype=torch.float32, device=vw.device)
+        if self._shard_out is None or self._shard_out[0].shape != (per, D) or self._shard_out[0].device != vw.device:
+            # persistent buffers: the sharded step allocates nothing, so it can be captured into a CUDA graph
+            self._shard_out = (torch.zeros(per, D, dtype=torch.float32, device=vw.device),
+                               torch.empty(world * per, D, dtype=torch.float32, device=vw.device),
+                               torch.empty(max(k1 - k0, 1), vw.shape[1], dtype=torch.float32, device=vw.device))
+        local, full, cv = self._shard_out
         if k1 > k0:
             gnn._check_inference()
-            _, _, f = native.class_side(gnn.param_pack(), vw[k0:k1], ew[k0:k1], ci[k0:k1].contiguous(),
-                                        sn.prune_node_threshold, True, sn.remove_self_loop,
-                                        want_edges=not native.gnn_tensor_path(D, vw.shape[1]))
-            local[:k1 - k0] = f
-        full = torch.empty(world * per, D, dtype=torch.float32, device=vw.device)
+            want_edges = not native.gnn_tensor_path(D, vw.shape[1])
+            if want_edges and (self._shard_ce is None or self._shard_ce.shape[0] != k1 - k0):
+                self._shard_ce = torch.empty(k1 - k0, vw.shape[1], vw.shape[1], dtype=torch.float32, device=vw.device)
+            native.class_side(gnn.param_pack(), vw[k0:k1], ew[k0:k1], ci[k0:k1], sn.prune_node_threshold, True,
+                              sn.remove_self_loop, out=(cv, self._shard_ce if want_edges else None, local[:k1 - k0]),
+                              want_edges=want_edges)
+            self.atlas = {"class_vertices": cv, "class_edges": None, "class_ingredients": ci[k0:k1], "class_range": (k0, k1)}
         dist.all_gather_into_tensor(full, local)              # the path's only collective: K*D*4 bytes over NVLink
         return full[:K]
 
@@ -118,6 +127,8 @@ class SchemaHead:
         """attn/attn_cls: raw head-averaged logits [bs, L, L] / [bs, L]; or `extracted` [bs*H, L+1, L+1] (the
         backbone tap), in which case the head mean is fused into the graph-build read."""
         sn = self.schema_net
+        if sn.remove_self_loop:     # the reference cannot build instance edges with this flag (large_scale_feat_to_e.cpp:136-139)
+            raise RuntimeError("diagonal dimensions cannot be identical 1, 1")
         T, bs, _ = mid_feat.shape
         L = T - 1
         graphs, ingredients = self.ws.get(bs, L, mid_feat.device)
@@ -141,7 +152,7 @@ class SchemaHead:
                 self._class_cache, self._class_cache_key = None, key
         if cache_class and self._class_cache is not None:
             f_kg = self._class_cache
-        elif self.overlap_class_side and self.class_shard is None:
+        elif self.overlap_class_side:
             main = torch.cuda.current_stream(mid_feat.device)
             if self._class_stream is None:
                 self._class_stream = torch.cuda.Stream(device=mid_feat.device)
@@ -173,9 +184,8 @@ class GraphedHead:
     an optimiser step between replays is honoured."""
 
     def __init__(self, head: "SchemaHead", mid_feat: torch.Tensor, attn: torch.Tensor, attn_cls: torch.Tensor, warmup: int = 2):
-        if head.class_shard is not None:
-            raise RuntimeError("GraphedHead: the class-sharded head issues an NCCL all-gather per step; capture the "
-                               "batch-sharded configuration (class_shard=None) or call the head eagerly")
+        # (a class-sharded head issues one NCCL all-gather per step on the class-side stream: NCCL collectives are
+        # graph-capturable, every rank captures and replays the same sequence)
         self.head, self.inputs = head, (mid_feat, attn, attn_cls)
         for _ in range(max(1, warmup)):          # lazy initialisation (workspaces, function attributes) outside the capture
             head(mid_feat, attn, attn_cls)
@@ -207,6 +217,7 @@ class HostPipeline:
         self.compute_done = [torch.cuda.Event() for _ in range(slots)]
         self.d2h_done = [torch.cuda.Event() for _ in range(slots)]
         self.out_host = [None] * slots
+        self.slot_ticket = [-1] * slots         # which submit() currently owns the slot's output buffer
         self.ticket = 0
 
     def submit(self, mid_feat: torch.Tensor, attn: torch.Tensor, attn_cls: torch.Tensor) -> int:
@@ -230,10 +241,14 @@ class HostPipeline:
             self.out_host[s] = torch.empty(pred.shape, dtype=pred.dtype).pin_memory()
         self.out_host[s].copy_(pred, non_blocking=True)
         self.d2h_done[s].record(main)
+        self.slot_ticket[s] = self.ticket
         self.ticket += 1
         return self.ticket - 1
 
     def result(self, ticket: int) -> torch.Tensor:
         s = ticket % self.slots
+        if self.slot_ticket[s] != ticket:
+            raise RuntimeError(f"HostPipeline.result({ticket}): that batch's output slot was reused by submit #{self.slot_ticket[s]}; "
+                               f"collect a result before submitting {self.slots} more batches")
         self.d2h_done[s].synchronize()
         return self.out_host[s]

@@ -23,7 +23,7 @@ SYMBOLS = [
     "sh_abi_version", "sh_last_error", "sh_launch_count", "sh_device_info", "sh_profile_enable", "sh_profile_collect",
     "sh_dev_attention_prologue",
     "sh_discretize_workspace_bytes", "sh_dev_discretize", "sh_discretize_stats",
-    "sh_dev_instance_graphs", "sh_dev_feat_to_v_attr", "sh_dev_feat_to_e",
+    "sh_dev_instance_graphs", "sh_dev_feat_to_v_attr", "sh_dev_feat_to_e", "sh_dev_class_accumulate",
     "sh_dev_class_atlas",
     "sh_gnn_workspace_bytes", "sh_dev_gnn_forward", "sh_dev_similarity", "sh_class_side_workspace_bytes",
     "sh_dev_class_side", "sh_dev_gnn_forward_class",
@@ -67,6 +67,7 @@ def lib():
         L.sh_dev_instance_graphs.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
         L.sh_dev_feat_to_v_attr.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
         L.sh_dev_feat_to_e.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
+        L.sh_dev_class_accumulate.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
         L.sh_dev_class_atlas.argtypes = [vp, vp, i32, i32, f32, i32, i32, vp, vp, vp]
         L.sh_dev_gnn_forward.argtypes = [ctypes.POINTER(GnnParams), i32, i32, vp, vp, vp, i32, vp, i64, i32, vp, vp, vp,
                                          ctypes.c_size_t, vp]
@@ -155,10 +156,13 @@ _ws_cache = {}
 
 
 def _workspace(key, nbytes, device):
-    ws = _ws_cache.get((key, device))
+    """Scratch memory of one kind of call, per device AND per launching stream: two heads driven from two streams of one
+    process never share scratch (calls on one stream are ordered, so sharing there is safe)."""
+    k = (key, device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(k)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
-        _ws_cache[(key, device)] = ws
+        _ws_cache[k] = ws
     return ws
 
 
@@ -261,10 +265,26 @@ def feat_to_e(ingredients, attn, geo_sim, class_ingredients, label, n_max, mean)
     ingredients = _i64c(ingredients)
     B, L = ingredients.shape
     K = class_ingredients.shape[0]
+    if label.numel() and (int(label.min()) < 0 or int(label.max()) >= K):
+        raise IndexError(f"feat_to_e: label out of range [0, {K})")       # the kernel indexes class rows unchecked
     out = torch.empty(B, n_max, n_max, 2, dtype=torch.float32, device=ingredients.device)
     check(lib().sh_dev_feat_to_e(ptr(ingredients), ptr(_f32c(attn)), ptr(_f32c(geo_sim)), ptr(_i64c(class_ingredients)),
                                  ptr(_i64c(label)), B, L, K, n_max, int(mean), ptr(out), stream()))
     return out
+
+
+def class_accumulate(x, label, acc, n_tracked=None):
+    """scripts/init_schema_net.py:31-34,57-59: acc[label[b]] += x[b] (batch order), n_tracked[label[b]] += 1; in place."""
+    require_cuda(x, label, acc, n_tracked)
+    x, label = _f32c(x), _i64c(label)
+    B, K = x.shape[0], acc.shape[0]
+    N = x[0].numel()
+    if acc.dtype != torch.float32 or not acc.is_contiguous() or acc[0].numel() != N:
+        raise RuntimeError("class_accumulate: acc must be a contiguous float32 [K, ...sample shape] tensor")
+    if label.numel() != B:
+        raise RuntimeError("class_accumulate: one label per sample")
+    check(lib().sh_dev_class_accumulate(ptr(x), ptr(label), B, N, K, ptr(acc), ptr(n_tracked), stream()))
+    return acc
 
 
 def class_atlas(vertex_weights, edge_weights, prune_threshold=None, prune_in_place=True, remove_self_loop=False,

@@ -2,7 +2,10 @@
 the oracle on seeded inputs, and -- at BASELINE.json's full sizes -- through size-independent properties.
 
 Bars (north star): codeword indices, vertex ids and zero patterns bit-exact; vertex weights, edge weights and logits
-within 1e-5 relative (fp32 accumulation).  `rel_close` measures max|a-b| / max|ref| per tensor.
+within 1e-5 relative (fp32 accumulation).  Two metrics, both written here: `rel_close` = max|a-b| / max|ref| per tensor
+(logits, class embeddings: entries of one tensor share a scale and cancel against each other); `elem_close` = element by
+element, |a-b| <= rtol * max(|ref|, floor * max|ref|) (vertex and edge weights: every entry is a weight in its own
+right; the floor, 1e-3 of the tensor's largest entry, only keeps entries that are numerically zero from dividing by ~0).
 """
 import os
 import sys
@@ -31,6 +34,17 @@ def rel_close(a, b, rtol=RTOL, what=""):
         return
     err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
     assert err <= rtol, f"{what}: max err / max|ref| = {err:.3e} > {rtol}"
+
+
+def elem_close(a, b, rtol=RTOL, floor=1e-3, what=""):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if a.size == 0:
+        return
+    scale = np.maximum(np.abs(b), floor * np.abs(b).max())
+    err = (np.abs(a - b) / np.maximum(scale, 1e-300)).max()
+    assert err <= rtol, f"{what}: max elementwise relative err = {err:.3e} > {rtol}"
 
 
 def build_modules(g=None, schema=None, gnn=None, M=None, K=None, Vc=None, D=None, dev="cuda"):
@@ -79,10 +93,12 @@ def test_golden_schema_net_and_matcher_modules(name):
     assert [len(x) for x in inst["instance_ingredients"]] == sizes.tolist()
     assert np.array_equal(torch.cat(inst["instance_ingredients"]).cpu().numpy(), g["inst_ids_cat"])
     rel_close(torch.cat(inst["instance_vertices"]), g["inst_w_cat"], what="vertex weights")
+    elem_close(torch.cat(inst["instance_vertices"]), g["inst_w_cat"], what="vertex weights (elementwise)")
     e = torch.cat([x.reshape(-1) for x in inst["instance_edges"]]).cpu().numpy()
     assert np.array_equal(e == 0, g["inst_e_cat"] == 0), "edge zero pattern"
     for a, b in zip(split_cat(e, sizes, True), split_cat(g["inst_e_cat"], sizes, True)):
         rel_close(a, b, what="edges")
+        elem_close(a, b, what="edges (elementwise)")
     # the reference's in-place clamp side effect on the caller's tensors (schema_net.py:296,335)
     ref_attn = torch.from_numpy(g["attn"]).clone()
     ref_attn.masked_fill_(ref_attn < -1.0, float("-inf"))
@@ -420,8 +436,10 @@ def test_full_head_vs_oracle_cfg1(cfg):
     assert n == [len(x) for x in ref["instance_ingredients"]]
     assert torch.equal(torch.cat(ids).cpu(), torch.cat(ref["instance_ingredients"]))
     rel_close(torch.cat(vw), torch.cat(ref["instance_vertices"]), what="vertices")
+    elem_close(torch.cat(vw), torch.cat(ref["instance_vertices"]), what="vertices (elementwise)")
     for a, b in zip(ed, ref["instance_edges"]):
         rel_close(a, b, what="edges")
+        elem_close(a, b, what="edges (elementwise)")
     rel_close(out["pred"], ref["pred"], what="logits")
     # the raw-heads entry (stage 0 fused into the graph-build read) gives the same answer
     H = c["H"]
@@ -608,6 +626,73 @@ def test_large_config_slices_vs_oracle(name, B, K):
     rel_close(out["pred"], ref["pred"], what=f"{name} logits")
     rel_close(out["feat_class"], ho.gnn_forward(gnn, ref["class_vertices"], ref["class_edges"], ref["class_ingredients"]),
               what=f"{name} class embeddings")
+
+
+def test_full_head_vs_oracle_cfg2():
+    """BASELINE configs[1] at FULL size (B=256, d=384, M=1024, K=100, Vc=1024, D=256) -- the configuration bench.py times.
+    Every stage against the oracle: 200+ class-side and 256 instance-side GEMM work units over 74 CTA pairs, i.e. the
+    persistent multi-tile path (shared-memory ring phases and the TMEM double buffer wrap across tiles)."""
+    from schemanet_b200.head import SchemaHead, GraphedHead
+    c = ho.CONFIGS["cfg2"]
+    vocab, mid, attn, attn_cls = ho.synth_inputs(c["B"], c["d"], c["M"], seed=1234)
+    schema = ho.synth_schema(c["M"], c["K"], c["Vc"], seed=1235)
+    gnn = ho.synth_gnn(c["M"], c["D"], seed=1236)
+    ref = ho.head_forward(mid, attn, attn_cls, vocab, dict(schema, edge_weights=schema["edge_weights"].clone()), gnn, ho.HEAD_CFG)
+    sn, m = build_modules(schema=schema, gnn=gnn, M=c["M"], K=c["K"], Vc=c["Vc"], D=c["D"])
+    head = SchemaHead(vocab.cuda(), sn, m)
+    dev_in = (mid.cuda(), attn.cuda(), attn_cls.cuda())
+    out = head(*dev_in)
+    assert torch.equal(out["ingredients"].cpu(), ref["ingredients"])
+    ids, vw, ed, n = out["graphs"].to_lists()
+    assert n == [len(x) for x in ref["instance_ingredients"]]
+    assert torch.equal(torch.cat(ids).cpu(), torch.cat(ref["instance_ingredients"]))
+    elem_close(torch.cat(vw), torch.cat(ref["instance_vertices"]), what="cfg2 vertices")
+    for b in range(0, c["B"], 5):
+        assert torch.equal(ed[b].cpu() == 0, ref["instance_edges"][b] == 0), "edge zero pattern"
+        elem_close(ed[b], ref["instance_edges"][b], what="cfg2 edges")
+    f_kg = ho.gnn_forward(gnn, ref["class_vertices"], ref["class_edges"], ref["class_ingredients"])
+    rel_close(out["feat_class"], f_kg, what="cfg2 class embeddings")
+    rel_close(out["pred"], ref["pred"], what="cfg2 logits")
+    # the CUDA-graph replay bench.py times returns the same logits
+    gh = GraphedHead(head, *dev_in)
+    rel_close(gh.replay()["pred"], ref["pred"], what="cfg2 logits (graph replay)")
+
+
+@pytest.mark.parametrize("side,G,n,D", [("class", 48, 1024, 256), ("instance", 160, 196, 256), ("class", 24, 500, 1024)])
+def test_gnn_more_tiles_than_cta_pairs(side, G, n, D):
+    """gemm3x_kernel is persistent: with more work units than CTA pairs (74 on a B200) every CTA walks several tiles.
+    class: 48 x 4 = 192 units of 256 rows (fused class side incl. the pruned-vertex tables); instance: 160 graphs;
+    wide: D=1024 has 4 column tiles per row block."""
+    from schemanet_b200 import native
+    from schema_inference.graph import GNN, Matcher
+    M = 1200
+    params = ho.synth_gnn(M, D, seed=31)
+    if side == "class":
+        sch = ho.synth_schema(M, G, n, seed=32)
+        gnn = GNN(M, D, num_layers=2).cuda()
+        gnn.load_state_dict(params)
+        _, _, f = native.class_side(gnn.param_pack(), sch["vertex_weights"].cuda(), sch["edge_weights"].clone().cuda(),
+                                    sch["class_ingredients"].cuda(), 0.001, True, False, want_edges=False)
+        atlas = ho.class_atlas(sch["vertex_weights"], sch["edge_weights"].clone(), sch["class_ingredients"], 0.001, False)
+        want = ho.gnn_forward(params, atlas["class_vertices"], atlas["class_edges"], sch["class_ingredients"], None)
+        rel_close(f, want, what="class side, multi-tile")
+    else:
+        gen = torch.Generator().manual_seed(33)
+        m = Matcher("inner_product", M, dict(embed_dim=D, num_layers=2)).cuda()
+        m.gnn.load_state_dict(params)
+        sizes = torch.randint(100, n + 1, (G,), generator=gen)
+        sizes[0] = n
+        mask = torch.arange(n)[None, :] >= sizes[:, None]
+        nodes = torch.rand(G, n, generator=gen) / n
+        edges = torch.rand(G, n, n, generator=gen) / n
+        ids = torch.randint(0, M, (G, n), generator=gen)
+        nodes[mask] = 0
+        ids[mask] = M
+        edges = edges * (~mask)[:, :, None] * (~mask)[:, None, :]
+        want = ho.gnn_forward(params, nodes, edges, ids, mask)
+        with torch.no_grad():
+            got = m.gnn(nodes.cuda(), edges.cuda(), ids.cuda(), mask.cuda())
+        rel_close(got, want, what="instance side, multi-tile")
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -26,6 +26,9 @@ def _gnn(g):
 def rel_close(a, b, rtol=RTOL, what=""):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, what
+    if np.isnan(b).any():        # the reference itself emits NaN there (e.g. gradients of fully pruned edge rows): same pattern
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f"{what}: NaN pattern differs"
+        a, b = np.nan_to_num(a), np.nan_to_num(b)
     scale = np.maximum(np.abs(b).max(), 1e-30)
     err = np.abs(a - b).max() / scale if a.size else 0.0
     assert err <= rtol, f"{what}: max err / max|ref| = {err:.3e}"
@@ -141,3 +144,63 @@ def test_c_restatement_vs_reference_cpp():
     es = ho.feat_to_instance_e(ing, a, geo, w, True)
     for x, y in zip(es, es_ref):
         rel_close(x.numpy(), y.numpy(), rtol=5e-7, what="e")
+
+
+def _init_batches(g):
+    nb = int(g["cfg"][0])
+    return [{k: _t(g[f"batch{i}.{k}"]) for k in ("ingredients", "attn", "attn_cls", "label")} for i in range(nb)]
+
+
+def test_init_callers_match_reference():
+    """scripts/init_schema_net.py's two dataset passes over SchemaNet.feat_to_full_vertices / feat_to_limited_edges
+    (fixture: the reference's own functions and classes, oracle/gen_golden.py::run_init_callers_case)."""
+    g = load_golden("init_callers")
+    nb, B, M, K, Vc = g["cfg"].tolist()
+    w_v, w_e = _t(g["w_v"]), _t(g["w_e"])
+    batches = _init_batches(g)
+    clamp = ho.HEAD_CFG["clamp_vertex_attn"]
+    full0 = ho.feat_to_full_vertices(batches[0]["ingredients"], batches[0]["attn_cls"], M, w_v, clamp)
+    rel_close(full0.numpy(), g["full_vertices0"], 2e-6, "feat_to_full_vertices")
+    cv = ho.init_class_vertices(batches, K, M, w_v, clamp)
+    rel_close(cv.numpy(), g["class_vertices_full"], 2e-6, "init_class_vertices")
+    init_w, valid = cv.topk(Vc, dim=1)
+    assert np.array_equal(valid.numpy(), g["valid_vertices"])
+    ci = _t(g["valid_vertices"])
+    lim0 = ho.feat_to_limited_edges(batches[0]["ingredients"], batches[0]["attn"], ci, batches[0]["label"], w_e,
+                                    ho.HEAD_CFG["clamp_edge_attn"])
+    rel_close(lim0.numpy(), g["limited_edges0"], 2e-6, "feat_to_limited_edges")
+    assert np.array_equal(lim0.numpy() == 0, g["limited_edges0"] == 0)
+    schema = dict(vertex_weights=_t(g["vertex_weights"]).clone(), edge_weights=_t(g["edge_weights_init"]).clone(),
+                  w_v=w_v.clone(), w_e=w_e.clone())
+    ho.init_graph(batches, schema["edge_weights"], ci, w_e, ho.HEAD_CFG["clamp_edge_attn"])
+    ho.schema_normalize(schema)
+    rel_close(schema["edge_weights"].numpy(), g["edge_weights_final"], 2e-6, "init_graph + normalize: edges")
+    rel_close(schema["vertex_weights"].numpy(), g["vertex_weights_final"], 2e-6, "init_graph + normalize: vertices")
+
+
+def test_train_step_matches_reference():
+    """One training iteration (normalize, forward in grad mode, SchemaInferenceLoss, backward) against the loss terms and
+    parameter gradients of the unmodified reference classes (oracle/gen_golden.py::run_train_case)."""
+    g = load_golden("train_step")
+    schema, gnn = _schema(g), _gnn(g)
+    schema = {k: v.clone() for k, v in schema.items()}
+    ho.schema_normalize(schema)
+    names = {"vertex_weights": "vertex_weights.tensor", "edge_weights": "edge_weights.tensor",
+             "w_v": "vertex_attribute_weights.tensor", "w_e": "edge_attribute_weights.tensor"}
+    for k, ref_name in names.items():
+        assert np.array_equal(schema[k].numpy(), g["after_normalize." + ref_name])
+        schema[k].requires_grad_(True)
+    gnn = {k: v.clone().requires_grad_(True) for k, v in gnn.items()}
+    pred, atlas = ho.train_forward(_t(g["ingredients"]), _t(g["attn"]), _t(g["attn_cls"]), schema, gnn, ho.HEAD_CFG)
+    rel_close(pred.detach().numpy(), g["pred"], what="train-mode logits")
+    terms = ho.schema_inference_loss(pred, atlas["class_vertices"], atlas["class_edges"], _t(g["label"]), 3.0, 4.0)
+    for k, v in terms.items():
+        assert abs(v.item() - g["loss." + k][0]) <= 1e-5 * max(1.0, abs(g["loss." + k][0])), k
+    total = terms["cls"] + 0.5 * terms["re_entropy_vertex"] + 0.75 * terms["re_entropy_edge"]
+    total.backward()
+    # gradient bar: 1e-4 of the tensor's largest entry (gradients are sums of cancelling fp32 terms -- the two attribute
+    # weights in particular, whose channels are each row-normalised; the forward quantities above keep the 1e-5 bar)
+    for k, ref_name in names.items():
+        rel_close(schema[k].grad.numpy(), g["grad.schema_net." + ref_name], 1e-4, "grad " + k)
+    for k, v in gnn.items():
+        rel_close((v.grad if v.grad is not None else torch.zeros_like(v)).numpy(), g["grad.matcher.gnn." + k], 1e-4, "grad gnn." + k)
