@@ -16,17 +16,30 @@
 
 namespace sh {
 
-// |row|^2 of a row-major [rows, d] matrix, one warp per row
+// |row|^2 of a row-major [rows, d] matrix, one warp per row; optionally also the squared norm of what truncating every
+// element to tf32 (10 mantissa bits) drops -- the operand residual the tensor-core path's candidate band is built from
+// (resid per row, and/or the running maximum of its bit pattern over the rows)
 __global__ void __launch_bounds__(256) row_sqnorm_kernel(const float *__restrict__ x, int64_t rows, int d,
-                                                         float *__restrict__ out)
+                                                         float *__restrict__ out, float *__restrict__ resid,
+                                                         unsigned *max_resid_bits)
 {
     const int lane = threadIdx.x & 31;
     for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
         const float *p = x + r * d;
-        float s = 0.0f;
-        for (int k = lane; k < d; k += kWarp) s = fmaf(p[k], p[k], s);
+        float s = 0.0f, e = 0.0f;
+        for (int k = lane; k < d; k += kWarp) {
+            const float v = p[k];
+            s = fmaf(v, v, s);
+            const float t = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            e = fmaf(t, t, e);
+        }
         s = warp_sum(s);
-        if (lane == 0) out[r] = s;
+        e = warp_sum(e) * 1.0000005f;
+        if (lane == 0) {
+            if (out) out[r] = s;
+            if (resid) resid[r] = e;
+            if (max_resid_bits) atomicMax(max_resid_bits, __float_as_uint(fabsf(e)));
+        }
     }
 }
 
@@ -138,10 +151,10 @@ discretize_exact_kernel(const float *__restrict__ X, const float *__restrict__ C
     }
 }
 
-int launch_row_sqnorm(const float *x, int64_t rows, int d, float *out, cudaStream_t st)
+int launch_row_sqnorm(const float *x, int64_t rows, int d, float *out, cudaStream_t st, float *resid, unsigned *max_resid_bits)
 {
     const int grid = (int)min(ceil_div64(rows, 8), (int64_t)sm_count() * 16);
-    SH_LAUNCH("row_sqnorm_kernel", st, row_sqnorm_kernel<<<grid, 256, 0, st>>>(x, rows, d, out));
+    SH_LAUNCH("row_sqnorm_kernel", st, row_sqnorm_kernel<<<grid, 256, 0, st>>>(x, rows, d, out, resid, max_resid_bits));
     SH_CHECK_LAUNCH();
     return 0;
 }

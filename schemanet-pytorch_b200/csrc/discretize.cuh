@@ -46,7 +46,8 @@ inline DiscWorkspace carve_disc_workspace(void *base, int64_t R, int M, int d)
     return w;
 }
 
-int launch_row_sqnorm(const float *x, int64_t rows, int d, float *out, cudaStream_t st);
+int launch_row_sqnorm(const float *x, int64_t rows, int d, float *out, cudaStream_t st, float *resid = nullptr,
+                      unsigned *max_resid_bits = nullptr);
 // |c_j|^2 into ws.cn (+inf padding up to a multiple of 256) and max_j |c_j|^2 into ws.counters[2]
 int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws, cudaStream_t st);
 int launch_gather(const float *vocab, const int64_t *idx, int64_t idx_rows, int64_t idx_row_stride,

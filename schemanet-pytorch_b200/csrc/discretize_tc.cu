@@ -46,7 +46,7 @@ struct DiscTcArgs {
     int num_m_blocks, num_n_blocks, num_k_blocks;
     const float *cn;       // [M padded to the N tile] |c_j|^2, +inf beyond M
     const float *xn;       // [R]  |x_r|^2
-    const float *xe;       // [R]  |x_r - fp16(x_r)|^2 (half operands; unused with tf32 operands)
+    const float *xe;       // [R]  |x_r - fp16(x_r)|^2 (half operands) or |x_r - trunc_tf32(x_r)|^2 (tf32 operands)
     const unsigned *cmax_bits;   // bit patterns of max_j |c_j|^2 and ([1]) max_j |c_j - fp16(c_j)|^2
     float gamma;           // accumulation error coefficient: |tc dot - exact dot of the rounded operands| <= gamma |x^| |c^|
     int debug;             // bit 0: epilogue skips its compute, bit 1: MMA issuer skips the MMAs (timing experiments)
@@ -196,9 +196,9 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         constexpr uint32_t kIdxDelta = 2u * TC_BM * kCandStride * 4u;   // byte distance cand_s -> cand_i
         (void)my_i;
         constexpr int kChunksPerHalf = (BN / 32) / 2;
-        const float cmax2 = __uint_as_float(a.cmax_bits[0]);
-        // tf32 operands: the hardware keeps 10 mantissa bits of each element, |dx_k| <= 2^-10 |x_k| whatever its rounding
-        const float dcmax2 = kHalf ? __uint_as_float(a.cmax_bits[1]) : cmax2 * 9.5367431640625e-7f;
+        // (tf32 operands: the residuals are those of truncation to 10 mantissa bits, an upper bound element by element of what
+        // the hardware drops whether it truncates or rounds)
+        const float cmax2 = __uint_as_float(a.cmax_bits[0]), dcmax2 = __uint_as_float(a.cmax_bits[1]);
         const float cmax = sqrtf(cmax2), dcmax = sqrtf(dcmax2);
         int as = 0;
         uint32_t aphase = 0;
@@ -211,7 +211,7 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // or infinite band: no candidate or every candidate is kept, and either way the row is rescanned exactly.
             float band = 0.0f;
             if (valid) {
-                const float xn2 = a.xn[row], xe2 = kHalf ? a.xe[row] : xn2 * 9.5367431640625e-7f;
+                const float xn2 = a.xn[row], xe2 = a.xe[row];
                 const float nx = sqrtf(xn2), dx = sqrtf(xe2), nxh = nx + dx;
                 const float e = dx * cmax + nxh * dcmax + a.gamma * nxh * (cmax + dcmax);
                 band = 4.0f * e + 1.9073486328125e-6f * (xn2 + cmax2);
@@ -490,7 +490,8 @@ int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M
     } else {
         if (make_tmap_f32(&tmA, X, (uint64_t)d, (uint64_t)R, 1, (uint64_t)d, 0, TC_BM)) return 1;
         if (make_tmap_f32(&tmB, C, (uint64_t)d, (uint64_t)M, 1, (uint64_t)d, 0, (uint32_t)(BN / b_split))) return 1;
-        if (launch_row_sqnorm(X, R, d, ws.xn, st)) return 1;
+        if (launch_row_sqnorm(X, R, d, ws.xn, st, ws.xe, nullptr)) return 1;
+        if (launch_row_sqnorm(C, M, d, nullptr, st, nullptr, (unsigned *)(ws.counters + 2) + 1)) return 1;
     }
     DiscTcArgs a{};
     a.R = R; a.d = d; a.M = M;

@@ -9,8 +9,10 @@
 // lo = x - hi (exact in fp32, 13 significant bits), and each product is accumulated as
 //       a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi        (three kind::tf32 MMAs into the same fp32 TMEM accumulator)
 // which leaves a relative error of ~2^-21 per product -- the same order as fp32 FMA accumulation itself.
-// The hi/lo pairs are produced by the kernels that write the operands (adjacency prep, embedding gather, the previous
-// GEMM's epilogue), so the GEMM main loop is pure TMA -> tcgen05.mma.
+// Operands live in HBM ONCE, as plain fp32: TMA brings the fp32 tile into the stage's "hi" slot and four transform warps
+// split it in place (hi overwrites the tile, lo goes to the slot next to it; element positions are unchanged, so the
+// 128-byte swizzle TMA applied is preserved) before the MMA warp is released.  Round 1 stored every operand as a hi/lo
+// pair in HBM: twice the bytes on every producer and on every GEMM read, which made the class-side GEMMs HBM kernels.
 //
 // Per layer, for a batch of G graphs with n_g <= n_fixed nodes:
 //   adj GEMM     Y[g]  = Adj[g] (n x n, symmetric, K-major)  *  X[g]   given as X^T [D, n] (K-major)   -> Y  [n, D]
@@ -20,9 +22,10 @@
 // Layer 0 is shortened to ONE adjacency GEMM with bias + LayerNorm + ReLU in its epilogue (the first Linear is applied to
 // the (M+1)-row embedding table instead, see run_layers_tc); the last layer's epilogue emits vertex-weighted group sums
 // instead of activations.  Class graphs run on their un-pruned vertices only (class_perm_kernel, per-code tables).
-// Kernel layout: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5 epilogue; CTA pairs (cta_group::2, one
-// UMMA of M = 256 per pair, each CTA stages its 128 A rows and half of the B tile) with a 3-stage 64 KB shared-memory
-// ring per CTA, or single CTAs with a 2-stage 96 KB ring (SCHEMANET_GEMM_CTAS=1); 2-stage 256-column TMEM accumulator ring.
+// Kernel layout: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5 epilogue, warps 6-9 operand transform
+// (fp32 -> hi/lo in shared memory); CTA pairs (cta_group::2, one UMMA of M = 256 per pair, each CTA stages and splits its
+// 128 A rows and half of the B tile) with a 3-stage 64 KB shared-memory ring per CTA, or single CTAs with a 2-stage 96 KB
+// ring (SCHEMANET_GEMM_CTAS=1); 2-stage 256-column TMEM accumulator ring.
 #include <stdlib.h>
 #include "common.cuh"
 #include "gnn_tc.cuh"
@@ -35,10 +38,10 @@ using namespace tc;
 constexpr int G_BM = 128;
 constexpr int G_BN = 256;      // == embed_dim
 constexpr int G_BK = 32;
-constexpr int G_THREADS = 192;
+constexpr int G_THREADS = 320;
 constexpr int kABytes = G_BM * G_BK * 4;                 // 16 KB
 
-enum { EPI_STORE_SPLIT = 0, EPI_LN_RELU_T_SPLIT = 1, EPI_LN_RELU_ROWS = 2, EPI_BIAS_ROWS = 3 };
+enum { EPI_STORE_ROWS = 0, EPI_LN_RELU_T = 1, EPI_LN_RELU_ROWS = 2, EPI_BIAS_ROWS = 3 };
 constexpr int kMaxDim = 1024;   // largest embed_dim the bias staging buffer holds
 
 struct GemmTcArgs {
@@ -55,8 +58,8 @@ struct GemmTcArgs {
     int skip_masked;          // 1: work units whose rows are all >= their graph's size are skipped in every epilogue
                               // (nothing downstream reads those rows: class graphs reduced to their un-pruned vertices)
     // epilogue
-    float *out_hi, *out_lo;      // EPI_STORE_SPLIT: Y hi/lo [G, n_fixed, 256]; EPI_LN_RELU_T_SPLIT: H^T hi/lo [G, 256, ldk]
-    float *out_rows;             // EPI_LN_RELU_ROWS: H [G*n_fixed, 256]
+    float *out_t;                // EPI_LN_RELU_T: H^T [G, 256, ldk]
+    float *out_rows;             // EPI_STORE_ROWS: Y [G, n_fixed, N_total]; EPI_LN_RELU_ROWS / EPI_BIAS_ROWS: H / Z [rows, N_total]
     // EPI_LN_RELU_ROWS on flattened rows (G == 1) with pool_groups != null: instead of storing H, emit the vertex-weighted
     // column sums of every 32-row group, split at the (at most one) graph boundary inside the group:
     // pool_groups[group, 0 | 1, 256]  (slot 0: rows of the group's first graph, slot 1: rows of the next graph)
@@ -77,10 +80,8 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo)
 // A warp holds a 32 (rows, one per lane) x 32 (columns) fp32 chunk in registers (the TMEM layout).  Writing it row-major
 // straight from registers would issue 16-byte pieces of 32 different rows per instruction; going through a padded
 // shared-memory tile lets 8 lanes cover one 128-byte row segment, i.e. every store instruction writes 4 full lines.
-// kSplit: write hi/lo (x & 0xffffe000, x - hi) to two arrays instead of x to one.
-template <bool kSplit>
-__device__ __forceinline__ void store_chunk_rows(float *tile /* [32][33] */, const float (&v)[32], int lane, float *dst_hi,
-                                                 float *dst_lo, size_t row_stride, int rows_valid)
+__device__ __forceinline__ void store_chunk_rows(float *tile /* [32][33] */, const float (&v)[32], int lane, float *dst,
+                                                 size_t row_stride, int rows_valid)
 {
     __syncwarp();
 #pragma unroll
@@ -92,16 +93,21 @@ __device__ __forceinline__ void store_chunk_rows(float *tile /* [32][33] */, con
         const int r = r0 + sub;
         if (r < rows_valid) {
             const float *t = tile + r * 33 + c4;
-            const float4 x = make_float4(t[0], t[1], t[2], t[3]);
-            if (kSplit) {
-                float4 h, l;
-                split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-                *reinterpret_cast<float4 *>(dst_hi + (size_t)r * row_stride + c4) = h;
-                *reinterpret_cast<float4 *>(dst_lo + (size_t)r * row_stride + c4) = l;
-            } else {
-                *reinterpret_cast<float4 *>(dst_hi + (size_t)r * row_stride + c4) = x;
-            }
+            *reinterpret_cast<float4 *>(dst + (size_t)r * row_stride + c4) = make_float4(t[0], t[1], t[2], t[3]);
         }
+    }
+}
+
+// In-place operand split of `bytes` of a stage slot (hi overwrites, lo at +lo_off), 16 bytes per thread and step.
+__device__ __forceinline__ void split_region(uint32_t base, uint32_t lo_off, int bytes, int tid, int nthreads)
+{
+    for (int o = tid * 16; o < bytes; o += nthreads * 16) {
+        float4 x;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(base + o));
+        float4 h, l;
+        split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(base + o), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(base + o + lo_off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
     }
 }
 
@@ -123,8 +129,7 @@ struct GemmPlan {
 
 template <int EPI, int CTAS>
 __global__ void __launch_bounds__(G_THREADS, 1)
-gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-              const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, GemmTcArgs a)
+gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs a)
 {
     using P = GemmPlan<CTAS>;
     constexpr int S = P::kStages;
@@ -132,8 +137,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
     // 1 KB alignment for the 128-byte-swizzled TMA tiles, as an OFFSET into the shared array: going through uintptr_t makes
     // the compiler lose the address space and emit 64-bit generic LD/ST for every shared-memory access of the epilogue
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t *full = (uint64_t *)(smem + P::kBar);
-    uint64_t *empty = full + S;
+    uint64_t *full = (uint64_t *)(smem + P::kBar);       // TMA bytes of this CTA's slot have landed (local)
+    uint64_t *ready = full + S;                          // both CTAs' slots are split into hi/lo (lives in the leader)
+    uint64_t *empty = ready + S;
     uint64_t *tmem_full = empty + S;
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 2);
@@ -143,13 +149,13 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
     const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;     // 0 = the CTA that issues the MMAs
     const int unit = (int)blockIdx.x / CTAS, num_units = (int)gridDim.x / CTAS;
 
-    if (EPI == EPI_LN_RELU_T_SPLIT || EPI == EPI_LN_RELU_ROWS)
+    if (EPI == EPI_LN_RELU_T || EPI == EPI_LN_RELU_ROWS)
         for (int i = threadIdx.x; i < G_BN; i += G_THREADS) { s_bias[i] = a.bias[i]; s_gamma[i] = a.gamma[i]; s_beta[i] = a.beta[i]; }
     if (EPI == EPI_BIAS_ROWS)
         for (int i = threadIdx.x; i < a.N_total; i += G_THREADS) s_bias[i] = a.bias[i];
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
-        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4 * CTAS); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * CTAS); }
         fence_barrier_init();
     }
@@ -173,7 +179,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
         const int mb = ub * CTAS + rank;   /* this CTA's 128-row block */                                 \
         const int n_g = (a.k_sizes && a.G > 1) ? a.k_sizes[g] : a.K_total;                                \
         /* units past the graph are skipped, except when the epilogue must still write their (zero) rows */ \
-        if ((EPI == EPI_STORE_SPLIT || a.skip_masked) && a.G > 1 && !a.identity_tail && ub * UB >= n_g) continue; \
+        if ((EPI == EPI_STORE_ROWS || a.skip_masked) && a.G > 1 && !a.identity_tail && ub * UB >= n_g) continue; \
         if (a.skip_masked && a.G == 1 && a.row_sizes) {   /* flattened rows: unit inside one graph, past its size */ \
             const int r0_ = ub * UB, gi_ = r0_ / a.rows_per_graph;                                        \
             if ((r0_ + UB - 1) / a.rows_per_graph == gi_ && r0_ - gi_ * a.rows_per_graph >= a.row_sizes[gi_]) continue; \
@@ -200,21 +206,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *s = smem + stage * P::kStage;
                     const int gb = a.batched_b ? g : 0;
-                    if (CTAS == 1) {
-                        mbar_arrive_expect_tx(&full[stage], P::kStage);
-                        tma_load_3d(s, &tmAh, &full[stage], kb * G_BK, mb * G_BM, g);
-                        tma_load_3d(s + kABytes, &tmAl, &full[stage], kb * G_BK, mb * G_BM, g);
-                        tma_load_3d(s + 2 * kABytes, &tmBh, &full[stage], kb * G_BK, nb * G_BN, gb);
-                        tma_load_3d(s + 2 * kABytes + P::kBBytesL, &tmBl, &full[stage], kb * G_BK, nb * G_BN, gb);
-                    } else {
-                        // both CTAs' bytes complete on the LEADER's barrier (the only one the MMA issuer waits on)
-                        const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * P::kStage);
-                        tma_load_3d_pair(s, &tmAh, lead_full, kb * G_BK, mb * G_BM, g);
-                        tma_load_3d_pair(s + kABytes, &tmAl, lead_full, kb * G_BK, mb * G_BM, g);
-                        tma_load_3d_pair(s + 2 * kABytes, &tmBh, lead_full, kb * G_BK, nb * G_BN + rank * P::kBRows, gb);
-                        tma_load_3d_pair(s + 2 * kABytes + P::kBBytesL, &tmBl, lead_full, kb * G_BK, nb * G_BN + rank * P::kBRows, gb);
-                    }
+                    // every CTA loads its own fp32 tiles (128 A rows, its share of the B tile) into the hi slots and
+                    // tracks them on its OWN barrier: its transform warps wait there
+                    mbar_arrive_expect_tx(&full[stage], kABytes + P::kBBytesL);
+                    tma_load_3d(s, &tmA, &full[stage], kb * G_BK, mb * G_BM, g);
+                    tma_load_3d(s + 2 * kABytes, &tmB, &full[stage], kb * G_BK, nb * G_BN + rank * P::kBRows, gb);
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             TILE_LOOP_END
@@ -229,7 +225,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * G_BN);
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait_cluster(&ready[stage], phase);     // hi/lo of both CTAs' slots are in place
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t s = smem_u32(smem + stage * P::kStage);
@@ -262,7 +258,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                 if (++as == 2) { as = 0; aphase ^= 1; }
             TILE_LOOP_END
         }
-    } else {
+    } else if (warp < 6) {
         const int wq = warp & 3;
         const int row_in_tile = wq * 32 + lane;
         int as = 0;
@@ -272,18 +268,17 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * G_BN);
             const int m = mb * G_BM + row_in_tile;           // row inside this batch entry
-            if (EPI == EPI_STORE_SPLIT) {
-                // Y[g, m, :] as hi/lo (row-major: the K-major A operand of the linear GEMM)
+            if (EPI == EPI_STORE_ROWS) {
+                // Y[g, m, :] (row-major: the K-major A operand of the linear GEMM)
                 // warp-level view: this warp owns rows [mb*128 + wq*32, +32) of graph g
                 const int m_warp = mb * G_BM + wq * 32;
                 const int rows_valid = min(32, a.rows_per_graph - m_warp);
-                float *oh = a.out_hi + ((size_t)g * a.rows_per_graph + m_warp) * a.N_total + nb * G_BN;
-                float *ol = a.out_lo + ((size_t)g * a.rows_per_graph + m_warp) * a.N_total + nb * G_BN;
+                float *o = a.out_rows + ((size_t)g * a.rows_per_graph + m_warp) * a.N_total + nb * G_BN;
 #pragma unroll 1
                 for (int c = 0; c < G_BN / 32; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-                    store_chunk_rows<true>(s_out + wq * 32 * 33, v, lane, oh + c * 32, ol + c * 32, a.N_total, rows_valid);
+                    store_chunk_rows(s_out + wq * 32 * 33, v, lane, o + c * 32, a.N_total, rows_valid);
                 }
             } else if (EPI == EPI_BIAS_ROWS) {
                 // Z[m, nb*256 + :] = acc + bias (embed_dim > 256: LayerNorm needs the whole row and runs as its own kernel)
@@ -295,7 +290,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += s_bias[nb * G_BN + c * 32 + j];
-                    store_chunk_rows<false>(s_out + wq * 32 * 33, v, lane, o + c * 32, nullptr, a.N_total, min(32, a.M_total - m_warp));
+                    store_chunk_rows(s_out + wq * 32 * 33, v, lane, o + c * 32, a.N_total, min(32, a.M_total - m_warp));
                 }
             } else {
                 // z = acc + bias; LayerNorm over the 256 columns this thread owns; ReLU   (gnn.py:31,45)
@@ -379,21 +374,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                         // rows of masked nodes are never read downstream (pooling stops at n_g): store all rows in range
                         const int m_warp = mb * G_BM + wq * 32;
                         const size_t row0 = (a.G > 1 ? (size_t)g * a.rows_per_graph : 0) + m_warp;
-                        store_chunk_rows<false>(s_out + wq * 32 * 33, v, lane, a.out_rows + row0 * G_BN + c * 32, nullptr, G_BN,
-                                                min(32, (a.G > 1 ? a.rows_per_graph : a.M_total) - m_warp));
+                        store_chunk_rows(s_out + wq * 32 * 33, v, lane, a.out_rows + row0 * G_BN + c * 32, G_BN,
+                                         min(32, (a.G > 1 ? a.rows_per_graph : a.M_total) - m_warp));
                     } else {
-                        // H^T[gg, n, i] as hi/lo: lanes hold consecutive nodes i -> coalesced 128-byte stores; nodes
-                        // beyond n_g are written as zeros (they are the zero-padded K range of the next adj GEMM)
+                        // H^T[gg, n, i]: lanes hold consecutive nodes i -> coalesced 128-byte stores; nodes beyond n_g
+                        // are written as zeros (they are the zero-padded K range of the next adj GEMM)
                         if (in_range) {
-                            float *oh = a.out_hi + ((size_t)gg * G_BN + c * 32) * a.ldk + i;
-                            float *ol = a.out_lo + ((size_t)gg * G_BN + c * 32) * a.ldk + i;
+                            float *o = a.out_t + ((size_t)gg * G_BN + c * 32) * a.ldk + i;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float h, l;
-                                split_tf32(valid ? v[j] : 0.0f, h, l);
-                                oh[(size_t)j * a.ldk] = h;
-                                ol[(size_t)j * a.ldk] = l;
-                            }
+                            for (int j = 0; j < 32; ++j) o[(size_t)j * a.ldk] = valid ? v[j] : 0.0f;
                         }
                     }
                 }
@@ -405,6 +394,28 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
                 else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));   // the leader owns the accumulator ring
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
+        TILE_LOOP_END
+    } else {
+        // ===================== operand transform: fp32 tile -> hi / lo, in place =====================
+        const int tid = (int)threadIdx.x - 6 * 32;                  // 0 .. 127
+        const uint32_t ready_lead = mapa_u32(smem_u32(&ready[0]), 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        TILE_LOOP_BEGIN
+            (void)nb; (void)mb;
+            for (int kidx = 0; kidx < kblocks; ++kidx) {
+                mbar_wait(&full[stage], phase);                     // this CTA's fp32 tiles have landed
+                const uint32_t sb = smem_u32(smem + stage * P::kStage);
+                split_region(sb, kABytes, kABytes, tid, 128);
+                split_region(sb + 2 * kABytes, P::kBBytesL, P::kBBytesL, tid, 128);
+                fence_proxy_async();                                // generic-proxy stores -> visible to the UMMA (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    if (CTAS == 1) mbar_arrive(&ready[stage]);
+                    else mbar_arrive_cluster(ready_lead + (uint32_t)(stage * 8));
+                }
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
         TILE_LOOP_END
     }
 #undef TILE_LOOP_BEGIN
@@ -418,11 +429,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------------------------------
-// Adj = (E + E^T)/2 + I  (gnn.py:27-30) as hi/lo, zero outside the n_g x n_g corner.  32x32 tiles, the transposed tile
+// Adj = (E + E^T)/2 + I  (gnn.py:27-30), zero outside the n_g x n_g corner.  32x32 tiles, the transposed tile
 // goes through shared memory so that both reads are coalesced.
 __global__ void __launch_bounds__(256)
 adj_prep_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int32_t *__restrict__ sizes, int n_fixed,
-                int ldk, float *__restrict__ adj_hi, float *__restrict__ adj_lo)
+                int ldk, float *__restrict__ adj)
 {
     __shared__ float tile[32][33];
     const int g = blockIdx.z;
@@ -441,11 +452,7 @@ adj_prep_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const in
         if (i < n_fixed && j < ldk) {
             float v = 0.0f;
             if (i < n_g && j < n_g) v = (Eg[(size_t)i * ld + j] + tile[tx][r]) / 2.0f + (i == j ? 1.0f : 0.0f);
-            float h, l;
-            split_tf32(v, h, l);
-            const size_t o = ((size_t)g * n_fixed + i) * ldk + j;
-            adj_hi[o] = h;
-            adj_lo[o] = l;
+            adj[((size_t)g * n_fixed + i) * ldk + j] = v;
         }
     }
 }
@@ -454,19 +461,19 @@ adj_prep_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const in
 // so a WARP owns the tile pair (I, J) / (J, I), I <= J, reads both source tiles once (16 independent row loads per lane
 // in flight) and writes both results; the remaining items of a graph's work list are 32-row strips of zero padding.
 // ctas_per_graph CTAs of 4 warps walk each graph's list.  (One CTA per 32x32 tile was latency-bound: 0.045 ms for 118 MB.)
-__device__ __forceinline__ void adj_zero_strip(float *__restrict__ adj_hi, float *__restrict__ adj_lo, size_t base, int ldk,
-                                               int rows, int i0, int c0, int c1, int lane)
+__device__ __forceinline__ void adj_zero_strip(float *__restrict__ adj, size_t base, int ldk, int rows, int i0, int c0, int c1,
+                                               int lane)
 {
     const int nr = min(32, rows - i0);
     for (int j = c0 + lane; j < c1; j += 32) {
-        float *ph = adj_hi + base + (size_t)i0 * ldk + j, *pl = adj_lo + base + (size_t)i0 * ldk + j;
-        for (int r = 0; r < nr; ++r) { *ph = 0.0f; *pl = 0.0f; ph += ldk; pl += ldk; }
+        float *ph = adj + base + (size_t)i0 * ldk + j;
+        for (int r = 0; r < nr; ++r) { *ph = 0.0f; ph += ldk; }
     }
 }
 
 __global__ void __launch_bounds__(128)
 adj_sym_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int32_t *__restrict__ sizes, int n_fixed, int ldk,
-               float *__restrict__ adj_hi, float *__restrict__ adj_lo, int ctas_per_graph)
+               float *__restrict__ adj, int ctas_per_graph)
 {
     __shared__ float tiles[4][2][32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -482,7 +489,7 @@ adj_sym_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int
     for (int item = wid; item < pairs + TR; item += nw) {
         if (item >= pairs) {                 // zero padding right of (rows < n_g) / instead of (rows >= n_g) the corner
             const int i0 = (item - pairs) * 32;
-            adj_zero_strip(adj_hi, adj_lo, base, ldk, n_fixed, i0, i0 < n_g ? nt * 32 : 0, ldk, lane);
+            adj_zero_strip(adj, base, ldk, n_fixed, i0, i0 < n_g ? nt * 32 : 0, ldk, lane);
             continue;
         }
         int J = (int)((sqrtf(8.0f * (float)item + 1.0f) - 1.0f) * 0.5f);
@@ -503,7 +510,7 @@ adj_sym_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int
         }
         __syncwarp();
         const bool col_ok = j0 + lane < ldk;
-        float *ph = adj_hi + base + (size_t)i0 * ldk + j0 + lane, *pl = adj_lo + base + (size_t)i0 * ldk + j0 + lane;
+        float *ph = adj + base + (size_t)i0 * ldk + j0 + lane;
         const int diag = (I == J) ? lane : -1;
 #pragma unroll 1
         for (int rb = 0; rb < 32; rb += 16) {
@@ -518,42 +525,30 @@ adj_sym_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int
                 float sym = 0.0f;
                 if (r < nvi && vj) sym = (v[u] + T[lane][r]) / 2.0f + ((r == diag) ? 1.0f : 0.0f);
                 S[r][lane] = sym;
-                if (col_ok && i0 + r < n_fixed) {
-                    float h, l;
-                    split_tf32(sym, h, l);
-                    *ph = h;
-                    *pl = l;
-                }
+                if (col_ok && i0 + r < n_fixed) *ph = sym;
                 ph += ldk;
-                pl += ldk;
             }
         }
         __syncwarp();
         if (I != J && i0 + lane < ldk) {
-            ph = adj_hi + base + (size_t)j0 * ldk + i0 + lane;
-            pl = adj_lo + base + (size_t)j0 * ldk + i0 + lane;
+            ph = adj + base + (size_t)j0 * ldk + i0 + lane;
             const int rows = min(32, n_fixed - j0);
 #pragma unroll 4
             for (int r = 0; r < rows; ++r) {
-                float h, l;
-                split_tf32(S[lane][r], h, l);
-                *ph = h;
-                *pl = l;
+                *ph = S[lane][r];
                 ph += ldk;
-                pl += ldk;
             }
         }
         __syncwarp();
     }
 }
 
-// X0^T[g, d, i] = Emb[ids[g, i], d] as hi/lo (gnn.py:91), zero for i >= n_g.  One CTA per (32 nodes, 256 features, graph):
+// X0^T[g, d, i] = Emb[ids[g, i], d] (gnn.py:91), zero for i >= n_g.  One CTA per (32 nodes, 256 features, graph):
 // each warp reads whole 1 KB table rows (8 coalesced loads per node, the id fetched once), the slab is transposed through
 // shared memory and written as 128-byte row segments of X^T.
 __global__ void __launch_bounds__(256)
 embed_gather_t_kernel(const float *__restrict__ emb, const int64_t *__restrict__ ids, int ld_ids,
-                      const int32_t *__restrict__ sizes, int n_fixed, int ldk, int D, float *__restrict__ xt_hi,
-                      float *__restrict__ xt_lo)
+                      const int32_t *__restrict__ sizes, int n_fixed, int ldk, int D, float *__restrict__ xt)
 {
     __shared__ float tile[32][257];
     const int g = blockIdx.z;
@@ -572,19 +567,8 @@ embed_gather_t_kernel(const float *__restrict__ emb, const int64_t *__restrict__
     __syncthreads();
     const int i = i0 + lane;
     if (i >= ldk) return;
-    for (int d = warp; d < dn; d += 8) {               // feature d0 + d, nodes i0 .. i0 + 31 (coalesced along i)
-        float h, l;
-        split_tf32(tile[lane][d], h, l);
-        const size_t o = ((size_t)g * D + d0 + d) * ldk + i;
-        xt_hi[o] = h;
-        xt_lo[o] = l;
-    }
-}
-
-__global__ void __launch_bounds__(256) split_kernel(const float *__restrict__ x, int64_t n, float *__restrict__ hi, float *__restrict__ lo)
-{
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        split_tf32(x[i], hi[i], lo[i]);
+    for (int d = warp; d < dn; d += 8)                 // feature d0 + d, nodes i0 .. i0 + 31 (coalesced along i)
+        xt[((size_t)g * D + d0 + d) * ldk + i] = tile[lane][d];
 }
 
 constexpr int kTableSlices = 8;   // CTAs per class summing the pruned vertices' table rows (pool_table_rows_kernel)
@@ -765,12 +749,11 @@ class_perm_kernel(const float *__restrict__ cv, const int64_t *__restrict__ ci, 
     }
 }
 
-// Compacted class adjacency as hi/lo.  Only the parts the GEMM reads are written: the active corner (plus its padding
+// Compacted class adjacency.  Only the parts the GEMM reads are written: the active corner (plus its padding
 // up to the tile edges) and the 128x128 diagonal blocks of row blocks that contain inactive vertices.
 __global__ void __launch_bounds__(256)
 class_adj_prep_kernel(const float *__restrict__ ce, int K, int Vc, int ldk, int unit_rows, int with_tail,
-                      const int32_t *__restrict__ n_act, const int32_t *__restrict__ old_of_new, float *__restrict__ adj_hi,
-                      float *__restrict__ adj_lo)
+                      const int32_t *__restrict__ n_act, const int32_t *__restrict__ old_of_new, float *__restrict__ adj)
 {
     // One CTA per 32x32 tile; tiles outside the regions the GEMM reads exit at once.  (A persistent variant that walked
     // the tile space with two block barriers per tile measured 45 % slower.)
@@ -816,11 +799,7 @@ class_adj_prep_kernel(const float *__restrict__ ce, int K, int Vc, int ldk, int 
             if (pi < Vc && pj < ldk) {
                 float v = (pi == pj) ? 1.0f : 0.0f;
                 if (any_active && pi < nA && pj < nA) v = (direct[u] + tile[tx][r]) / 2.0f + v;
-                float h, l;
-                split_tf32(v, h, l);
-                const size_t o = ((size_t)k * Vc + pi) * ldk + pj;
-                adj_hi[o] = h;
-                adj_lo[o] = l;
+                adj[((size_t)k * Vc + pi) * ldk + pj] = v;
             }
         }
     }
@@ -838,19 +817,17 @@ constexpr int kAdjWarps = 4;
 constexpr int kAdjBatch = 16;   // gathered loads a lane keeps in flight (the kernel is bound by DRAM latency)
 
 // One 32-row strip of padding: columns [c0, c1) of rows [pi0, pi0 + 32) get the identity / zero pattern.
-__device__ __forceinline__ void adj_fill_strip(float *__restrict__ adj_hi, float *__restrict__ adj_lo, size_t base, int ldk,
-                                               int Vc, int pi0, int c0, int c1, int lane)
+__device__ __forceinline__ void adj_fill_strip(float *__restrict__ adj, size_t base, int ldk, int Vc, int pi0, int c0, int c1,
+                                               int lane)
 {
     c1 = min(c1, ldk);
     const int rows = min(32, Vc - pi0);
     for (int pj = c0 + lane; pj < c1; pj += 32) {
-        float *ph = adj_hi + base + (size_t)pi0 * ldk + pj, *pl = adj_lo + base + (size_t)pi0 * ldk + pj;
+        float *ph = adj + base + (size_t)pi0 * ldk + pj;
         const int diag = pj - pi0;          // row of this strip that holds the 1 of column pj
         for (int r = 0; r < rows; ++r) {
             *ph = (r == diag) ? 1.0f : 0.0f;
-            *pl = 0.0f;
             ph += ldk;
-            pl += ldk;
         }
     }
 }
@@ -858,8 +835,7 @@ __device__ __forceinline__ void adj_fill_strip(float *__restrict__ adj_hi, float
 __global__ void __launch_bounds__(kAdjWarps * 32)
 class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ rowinv, int K, int Vc, int ldk, int unit_rows,
                      int with_tail, int remove_self_loop, const int32_t *__restrict__ n_act,
-                     const int32_t *__restrict__ old_of_new, float *__restrict__ adj_hi, float *__restrict__ adj_lo,
-                     int ctas_per_class)
+                     const int32_t *__restrict__ old_of_new, float *__restrict__ adj, int ctas_per_class)
 {
     __shared__ float tiles[kAdjWarps][2][32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -883,11 +859,11 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
             const int pi0 = (item - pairs) * 32;
             const int act_end = pi0 < nA ? nt * 32 : 0;                 // columns [0, act_end) belong to tile pairs
             const int a_end = pi0 < rowsA ? colsA : 0;                  // region A: the active corner up to the tile edges
-            if (a_end > act_end) adj_fill_strip(adj_hi, adj_lo, base, ldk, Vc, pi0, act_end, a_end, lane);
+            if (a_end > act_end) adj_fill_strip(adj, base, ldk, Vc, pi0, act_end, a_end, lane);
             const int ub = pi0 / unit_rows;                             // region B: diagonal blocks with inactive vertices
             if (with_tail && (ub + 1) * unit_rows > nA) {
                 const int b0 = max(ub * unit_rows, max(act_end, a_end)), b1 = (ub + 1) * unit_rows;
-                if (b1 > b0) adj_fill_strip(adj_hi, adj_lo, base, ldk, Vc, pi0, b0, b1, lane);
+                if (b1 > b0) adj_fill_strip(adj, base, ldk, Vc, pi0, b0, b1, lane);
             }
             continue;
         }
@@ -923,7 +899,7 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
         __syncwarp();
         // this tile: S[r][lane] = (ce[old_i(r)][old_j(lane)] + ce[old_j(lane)][old_i(r)]) / 2 + identity
         const bool col_ok = pj0 + lane < ldk;
-        float *ph = adj_hi + base + (size_t)pi0 * ldk + pj0 + lane, *pl = adj_lo + base + (size_t)pi0 * ldk + pj0 + lane;
+        float *ph = adj + base + (size_t)pi0 * ldk + pj0 + lane;
         const int diag = (I == J) ? lane : -1;
 #pragma unroll 1
         for (int rb = 0; rb < 32; rb += kAdjBatch) {
@@ -939,29 +915,18 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
                 if (remove_self_loop && __shfl_sync(kFull, oi, r) == oj) e = 0.0f;
                 const float sym = (e + T[lane][r]) / 2.0f + ((r == diag) ? 1.0f : 0.0f);
                 S[r][lane] = sym;
-                if (col_ok && pi0 + r < Vc) {
-                    float h, l;
-                    split_tf32(sym, h, l);
-                    *ph = h;
-                    *pl = l;
-                }
+                if (col_ok && pi0 + r < Vc) *ph = sym;
                 ph += ldk;
-                pl += ldk;
             }
         }
         __syncwarp();
         if (I != J && pi0 + lane < ldk) {
-            ph = adj_hi + base + (size_t)pj0 * ldk + pi0 + lane;       // mirror tile (J, I)
-            pl = adj_lo + base + (size_t)pj0 * ldk + pi0 + lane;
+            ph = adj + base + (size_t)pj0 * ldk + pi0 + lane;          // mirror tile (J, I)
             const int rows = min(32, Vc - pj0);
 #pragma unroll 4
             for (int r = 0; r < rows; ++r) {
-                float h, l;
-                split_tf32(S[lane][r], h, l);
-                *ph = h;
-                *pl = l;
+                *ph = S[lane][r];
                 ph += ldk;
-                pl += ldk;
             }
         }
         __syncwarp();
@@ -973,13 +938,12 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
 // ---------------------------------------------------------------------------------------------------------------
 // embed_dim > 256: LayerNorm + ReLU as its own pass over Z = Y W^T + b (the GEMM epilogue cannot hold a row wider than
 // one 256-column accumulator).  One CTA per (32-node slab, graph); a warp normalises 4 rows (two-pass mean / variance).
-// kTranspose: stage the slab in shared memory and write H^T hi/lo for the next layer's adjacency GEMM (coalesced along
+// kTranspose: stage the slab in shared memory and write H^T for the next layer's adjacency GEMM (coalesced along
 // the node index, zeros for nodes >= n_g); otherwise overwrite Z with H in place (the pooling reads rows).
 template <bool kTranspose>
 __global__ void __launch_bounds__(256)
 ln_relu_wide_kernel(float *__restrict__ Z, const int32_t *__restrict__ row_sizes, int n_fixed, int ldk, int D,
-                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float *__restrict__ xt_hi,
-                    float *__restrict__ xt_lo)
+                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float *__restrict__ xt)
 {
     extern __shared__ float slab[];   // kTranspose: [32][D + 1]
     const int g = blockIdx.y, i0 = blockIdx.x * 32;
@@ -1008,13 +972,8 @@ ln_relu_wide_kernel(float *__restrict__ Z, const int32_t *__restrict__ row_sizes
         __syncthreads();
         const int i = i0 + lane;
         if (i < ldk)
-            for (int dd = warp; dd < D; dd += 8) {
-                float h, l;
-                split_tf32(i < n_fixed ? slab[lane * (D + 1) + dd] : 0.0f, h, l);
-                const size_t o = ((size_t)g * D + dd) * ldk + i;
-                xt_hi[o] = h;
-                xt_lo[o] = l;
-            }
+            for (int dd = warp; dd < D; dd += 8)
+                xt[((size_t)g * D + dd) * ldk + i] = i < n_fixed ? slab[lane * (D + 1) + dd] : 0.0f;
     }
 }
 
@@ -1026,7 +985,7 @@ bool gnn_tc_supported(int D, int n_fixed)
 }
 
 struct TcBuffers {
-    float *adj_hi, *adj_lo, *xt_hi, *xt_lo, *xt2_hi, *xt2_lo, *y_hi, *y_lo, *w_hi, *w_lo, *h_rows;
+    float *adj, *xt, *xt2, *y, *tab, *h_rows;     // tab: (M+1)-row table scratch (P_0 = Emb W_0^T), same size as y
     int32_t *n_act, *old_of_new;
     float *rowinv, *pool_extra, *pool_groups;
     int64_t *pid;
@@ -1042,17 +1001,12 @@ static TcBuffers carve_tc(void *base, int G, int n_fixed, int D)
     char *p = (char *)base;
     size_t off = 0;
     const size_t adj_b = al256((size_t)G * n_fixed * b.ldk * 4), xt_b = al256((size_t)G * D * b.ldk * 4);
-    const size_t y_b = al256((size_t)G * n_fixed * D * 4), w_b = al256((size_t)D * D * 4);
-    b.adj_hi = (float *)(p + off); off += adj_b;
-    b.adj_lo = (float *)(p + off); off += adj_b;
-    b.xt_hi = (float *)(p + off); off += xt_b;
-    b.xt_lo = (float *)(p + off); off += xt_b;
-    b.xt2_hi = (float *)(p + off); off += xt_b;
-    b.xt2_lo = (float *)(p + off); off += xt_b;
-    b.y_hi = (float *)(p + off); off += y_b;
-    b.y_lo = (float *)(p + off); off += y_b;
-    b.w_hi = (float *)(p + off); off += w_b;
-    b.w_lo = (float *)(p + off); off += w_b;
+    const size_t y_b = al256((size_t)G * n_fixed * D * 4);
+    b.adj = (float *)(p + off); off += adj_b;
+    b.xt = (float *)(p + off); off += xt_b;
+    b.xt2 = (float *)(p + off); off += xt_b;
+    b.y = (float *)(p + off); off += y_b;
+    b.tab = (float *)(p + off); off += y_b;
     b.h_rows = (float *)(p + off); off += y_b;
     b.n_act = (int32_t *)(p + off); off += al256((size_t)G * 4);
     b.old_of_new = (int32_t *)(p + off); off += al256((size_t)G * n_fixed * 4);
@@ -1105,14 +1059,14 @@ static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const c
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     prof_begin(name, st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm3x_kernel<EPI, CTAS>, maps[0], maps[1], maps[2], maps[3], a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm3x_kernel<EPI, CTAS>, maps[0], maps[1], a);
     prof_end(st);
     if (e != cudaSuccess) { set_error("%s launch -> %s", name, cudaGetErrorString(e)); return 1; }
     SH_CHECK_LAUNCH();
     return 0;
 }
 
-// maps: {A hi, A lo, B hi, B lo} for one CTA per row block, maps2: the same with 128-row B boxes for CTA pairs
+// maps: {A, B} for one CTA per row block, maps2: the same with 128-row B boxes for CTA pairs
 template <int EPI>
 static int launch_gemm3x(const CUtensorMap *maps, const CUtensorMap *maps2, const GemmTcArgs &a, const char *name, cudaStream_t st)
 {
@@ -1137,7 +1091,7 @@ static int tmap3(CUtensorMap *m, const float *p, uint64_t cols, uint64_t rows, u
     return 0;
 }
 
-// All GNN layers given a prepared hi/lo adjacency in b.adj_*.  k_sizes: active size per graph for the adjacency GEMM
+// All GNN layers given a prepared adjacency in b.adj.  k_sizes: active size per graph for the adjacency GEMM
 // (null = n_fixed); identity_tail: see GemmTcArgs; row_sizes: real rows per graph for masking (null = all).
 static bool layer0_fused(const sh_gnn_params *p, int G, int n_fixed)
 {
@@ -1183,15 +1137,15 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
         SH_CHECK_CUDA(cudaEventRecord(lane->fork, st));
         SH_CHECK_CUDA(cudaStreamWaitEvent(ts, lane->fork, 0));
     }
-    // P_0 = Emb W_0^T into y_lo; with a table tail the same launch also emits T_0 = relu(LN(P_0 + b_0)) into h_rows
-    if (launch_rows_linear(p->embedding, p->lin_w[0], p->num_codes + 1, D, b.y_lo, ts, p->lin_b[0], p->ln_w[0], p->ln_b[0],
+    // P_0 = Emb W_0^T into tab; with a table tail the same launch also emits T_0 = relu(LN(P_0 + b_0)) into h_rows
+    if (launch_rows_linear(p->embedding, p->lin_w[0], p->num_codes + 1, D, b.tab, ts, p->lin_b[0], p->ln_w[0], p->ln_b[0],
                            p->ln_eps, table_tail ? b.h_rows : nullptr))
         return 1;
     if (table_tail) {
-        // T_l ping-pongs between h_rows and y_hi: both are free until the GEMMs reach them, and the pooled sums of the
+        // T_l ping-pongs between h_rows and y: both are free until the GEMMs reach them, and the pooled sums of the
         // pruned vertices are taken (into pool_extra) before that
         const int rows = p->num_codes + 1;
-        float *cur = b.h_rows, *nxt = b.y_hi;
+        float *cur = b.h_rows, *nxt = b.y;
         for (int l = 1; l < p->num_layers; ++l) {
             if (launch_rows_linear(cur, p->lin_w[l], rows, D, nullptr, ts, p->lin_b[l], p->ln_w[l], p->ln_b[l], p->ln_eps, nxt))
                 return 1;
@@ -1204,7 +1158,7 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
         // X_0^T of the fused layer 0 (rows of P_0 gathered by node id): L2-write bound, it also runs under the HBM-read-bound
         // operand preparation
         dim3 grid2(ceil_div(b.ldk, 32), ceil_div(D, 256), G);
-        SH_LAUNCH("gnn_embed_gather", ts, embed_gather_t_kernel<<<grid2, 256, 0, ts>>>(b.y_lo, ids, ld_ids, row_sizes, n_fixed, b.ldk, D, b.xt_hi, b.xt_lo));
+        SH_LAUNCH("gnn_embed_gather", ts, embed_gather_t_kernel<<<grid2, 256, 0, ts>>>(b.tab, ids, ld_ids, row_sizes, n_fixed, b.ldk, D, b.xt));
         SH_CHECK_LAUNCH();
     }
     if (lane) SH_CHECK_CUDA(cudaEventRecord(lane->join, ts));
@@ -1230,39 +1184,30 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     // Layer-0 shortcut (embed_dim 256): (Adj X0) W0^T = Adj (X0 W0^T) and X0 = Emb[ids], so the first Linear is applied to
     // the (M+1)-row embedding TABLE once (a tiny fp32 GEMM) instead of to every node of every graph; layer 0 then is a
     // single adjacency GEMM with bias + LayerNorm + ReLU fused in its epilogue.  The table product is staged in the
-    // (still unused) Y_lo buffer, which it fits whenever the batch has at least M+1 node slots.
+    // `tab` buffer (as large as Y), which it fits whenever the batch has at least M+1 node slots.
     const bool fuse0 = layer0_fused(p, G, n_fixed);
     SH_REQUIRE(!table_tail || (fuse0 && row_sizes && !identity_tail), "run_layers_tc: table tail needs the fused layer 0");
-    const float *table = fuse0 ? b.y_lo : p->embedding;
+    const float *table = fuse0 ? b.tab : p->embedding;
     if (tables_join(p, G, n_fixed, st, table_tail)) return 1;
     if (!fuse0) {      // (fused layer 0: already gathered from P_0 by tables_begin)
         dim3 grid2(ceil_div(ldk, 32), ceil_div(D, 256), G);
-        SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(table, ids, ld_ids, row_sizes, n_fixed, ldk, D, b.xt_hi, b.xt_lo));
+        SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(table, ids, ld_ids, row_sizes, n_fixed, ldk, D, b.xt));
         SH_CHECK_LAUNCH();
     }
-    CUtensorMap adjm[2], xtm[2], ym[2], wm[2];
-    if (tmap3(&adjm[0], b.adj_hi, n_fixed, n_fixed, G, ldk, (uint64_t)n_fixed * ldk, G_BM)) return 1;
-    if (tmap3(&adjm[1], b.adj_lo, n_fixed, n_fixed, G, ldk, (uint64_t)n_fixed * ldk, G_BM)) return 1;
-    if (tmap3(&ym[0], b.y_hi, D, (uint64_t)G * n_fixed, 1, D, 0, G_BM)) return 1;
-    if (tmap3(&ym[1], b.y_lo, D, (uint64_t)G * n_fixed, 1, D, 0, G_BM)) return 1;
-    if (tmap3(&wm[0], b.w_hi, D, D, 1, D, 0, G_BN)) return 1;
-    if (tmap3(&wm[1], b.w_lo, D, D, 1, D, 0, G_BN)) return 1;
-    CUtensorMap wm2[2];               // CTA pairs stage half of the B tile each
-    if (tmap3(&wm2[0], b.w_hi, D, D, 1, D, 0, G_BN / 2)) return 1;
-    if (tmap3(&wm2[1], b.w_lo, D, D, 1, D, 0, G_BN / 2)) return 1;
+    CUtensorMap adjm, ym;
+    if (tmap3(&adjm, b.adj, n_fixed, n_fixed, G, ldk, (uint64_t)n_fixed * ldk, G_BM)) return 1;
+    if (tmap3(&ym, b.y, D, (uint64_t)G * n_fixed, 1, D, 0, G_BM)) return 1;
     // node features ping-pong between two X^T buffers (a fused-LayerNorm adjacency GEMM must not overwrite its own B)
-    float *xin_hi = b.xt_hi, *xin_lo = b.xt_lo, *xout_hi = b.xt2_hi, *xout_lo = b.xt2_lo;
+    float *xin = b.xt, *xout = b.xt2;
     bool pooled_in_epilogue = false;
 
     for (int l = 0; l < p->num_layers; ++l) {
         const bool last = (l == p->num_layers - 1);
-        CUtensorMap xtm[2], xtm2[2];
-        if (tmap3(&xtm[0], xin_hi, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
-        if (tmap3(&xtm[1], xin_lo, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
-        if (tmap3(&xtm2[0], xin_hi, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN / 2)) return 1;
-        if (tmap3(&xtm2[1], xin_lo, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN / 2)) return 1;
-        CUtensorMap m1[4] = {adjm[0], adjm[1], xtm[0], xtm[1]};
-        CUtensorMap m1p[4] = {adjm[0], adjm[1], xtm2[0], xtm2[1]};
+        CUtensorMap xtm, xtm2;            // B operand of the adjacency GEMM: whole 256-row tile / half of it (CTA pairs)
+        if (tmap3(&xtm, xin, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
+        if (tmap3(&xtm2, xin, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN / 2)) return 1;
+        CUtensorMap m1[2] = {adjm, xtm};
+        CUtensorMap m1p[2] = {adjm, xtm2};
         GemmTcArgs a{};
         a.G = G; a.rows_per_graph = n_fixed; a.M_total = n_fixed; a.K_total = n_fixed; a.N_total = D;
         a.k_sizes = k_sizes; a.identity_tail = identity_tail; a.batched_b = 1; a.skip_masked = table_tail ? 1 : 0;
@@ -1270,27 +1215,27 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
             // H1 = relu(LN(Adj (X0 W0^T) + b0)) in one kernel
             a.row_sizes = row_sizes;
             a.bias = p->lin_b[0]; a.gamma = p->ln_w[0]; a.beta = p->ln_b[0]; a.eps = p->ln_eps;
-            a.out_hi = xout_hi; a.out_lo = xout_lo; a.ldk = ldk; a.out_rows = b.h_rows;
+            a.out_t = xout; a.ldk = ldk; a.out_rows = b.h_rows;
             if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
-            else { if (launch_gemm3x<EPI_LN_RELU_T_SPLIT>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
-            float *t;
-            t = xin_hi; xin_hi = xout_hi; xout_hi = t;
-            t = xin_lo; xin_lo = xout_lo; xout_lo = t;
+            else { if (launch_gemm3x<EPI_LN_RELU_T>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
+            float *t = xin; xin = xout; xout = t;
             continue;
         }
-        SH_LAUNCH("gnn_split_weights", st, split_kernel<<<64, 256, 0, st>>>(p->lin_w[l], (int64_t)D * D, b.w_hi, b.w_lo));
-        SH_CHECK_LAUNCH();
         // Y = Adj X
-        a.out_hi = b.y_hi; a.out_lo = b.y_lo;
-        if (launch_gemm3x<EPI_STORE_SPLIT>(m1, m1p, a, "gnn_adj_gemm_tc", st)) return 1;
-        // H = relu(LN(Y W^T + b))
+        a.out_rows = b.y;
+        if (launch_gemm3x<EPI_STORE_ROWS>(m1, m1p, a, "gnn_adj_gemm_tc", st)) return 1;
+        // H = relu(LN(Y W^T + b)); the weight matrix is read where it lies (split in shared memory like every operand)
+        SH_REQUIRE(((uintptr_t)p->lin_w[l] & 15) == 0, "gnn: Linear weights must be 16-byte aligned for TMA");
+        CUtensorMap wm, wm2;
+        if (tmap3(&wm, p->lin_w[l], D, D, 1, D, 0, G_BN)) return 1;
+        if (tmap3(&wm2, p->lin_w[l], D, D, 1, D, 0, G_BN / 2)) return 1;
         GemmTcArgs c{};
         c.G = 1; c.rows_per_graph = n_fixed; c.M_total = G * n_fixed; c.K_total = D; c.N_total = D; c.row_sizes = row_sizes; c.batched_b = 0;
         c.skip_masked = table_tail ? 1 : 0;
         c.bias = p->lin_b[l]; c.gamma = p->ln_w[l]; c.beta = p->ln_b[l]; c.eps = p->ln_eps;
-        c.out_hi = xin_hi; c.out_lo = xin_lo; c.ldk = ldk; c.out_rows = b.h_rows;
-        CUtensorMap m2[4] = {ym[0], ym[1], wm[0], wm[1]};
-        CUtensorMap m2p[4] = {ym[0], ym[1], wm2[0], wm2[1]};
+        c.out_t = xin; c.ldk = ldk; c.out_rows = b.h_rows;
+        CUtensorMap m2[2] = {ym, wm};
+        CUtensorMap m2p[2] = {ym, wm2};
         if (D == G_BN) {
             if (last) {
                 // weighted pooling fused into the epilogue: H of the last layer is never written
@@ -1298,14 +1243,14 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
                 pooled_in_epilogue = true;
                 if (launch_gemm3x<EPI_LN_RELU_ROWS>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1;
             }
-            else { if (launch_gemm3x<EPI_LN_RELU_T_SPLIT>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
+            else { if (launch_gemm3x<EPI_LN_RELU_T>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
         } else {
-            // wide embeddings: bias in the GEMM epilogue, LayerNorm + ReLU (+ transpose/split) as a separate pass
+            // wide embeddings: bias in the GEMM epilogue, LayerNorm + ReLU (+ transpose) as a separate pass
             if (launch_gemm3x<EPI_BIAS_ROWS>(m2, m2p, c, "gnn_linear_tc", st)) return 1;
             dim3 grid(ceil_div(ldk, 32), G);
             if (last) {
                 SH_LAUNCH("gnn_ln_relu_wide", st, ln_relu_wide_kernel<false><<<grid, 256, 0, st>>>(b.h_rows, row_sizes, n_fixed, ldk, D, p->ln_w[l],
-                                                                                                  p->ln_b[l], p->ln_eps, nullptr, nullptr));
+                                                                                                  p->ln_b[l], p->ln_eps, nullptr));
             } else {
                 const size_t smem = (size_t)32 * (D + 1) * sizeof(float);
                 static bool configured = false;
@@ -1314,7 +1259,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
                     configured = true;
                 }
                 SH_LAUNCH("gnn_ln_relu_wide", st, ln_relu_wide_kernel<true><<<grid, 256, smem, st>>>(b.h_rows, row_sizes, n_fixed, ldk, D, p->ln_w[l],
-                                                                                                    p->ln_b[l], p->ln_eps, xin_hi, xin_lo));
+                                                                                                    p->ln_b[l], p->ln_eps, xin));
             }
             SH_CHECK_LAUNCH();
         }
@@ -1344,11 +1289,11 @@ int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *si
     if (tables_begin(p, G, n_fixed, sizes, ids, ld_v, vertex_w, b, st, false)) return 1;
     if (getenv("SCHEMANET_ADJ_TILED") != nullptr) {
         dim3 grid(ceil_div(b.ldk, 32), ceil_div(n_fixed, 32), G);
-        SH_LAUNCH("gnn_adj_prep", st, adj_prep_kernel<<<grid, 256, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj_hi, b.adj_lo));
+        SH_LAUNCH("gnn_adj_prep", st, adj_prep_kernel<<<grid, 256, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj));
     } else {
         const int tr = ceil_div(n_fixed, 32);
         const int cpg = max(1, min(16, ceil_div(tr * (tr + 1) / 2 + tr, 4 * 4)));   // ~4 items per warp at full size
-        SH_LAUNCH("gnn_adj_prep", st, adj_sym_kernel<<<G * cpg, 128, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj_hi, b.adj_lo, cpg));
+        SH_LAUNCH("gnn_adj_prep", st, adj_sym_kernel<<<G * cpg, 128, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj, cpg));
     }
     SH_CHECK_LAUNCH();
     return run_layers_tc(p, G, n_fixed, sizes, 0, sizes, ids, ld_v, vertex_w, ld_v, b, chunks, partial, st, false, fin);
@@ -1383,7 +1328,7 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
     SH_LAUNCH("class_adj_prep_kernel", st,
               class_adj_prep_kernel<<<dim3(ceil_div(b.ldk, 32), ceil_div(Vc, 32), K), 256, 0, st>>>(
                   class_edges, K, Vc, b.ldk, G_BM * gemm_ctas(), class_table_tail(p, K, Vc) ? 0 : 1, b.n_act, b.old_of_new,
-                  b.adj_hi, b.adj_lo));
+                  b.adj));
     SH_CHECK_LAUNCH();
     return class_layers_tc(p, K, Vc, b, chunks, partial, st, fin);
 }
@@ -1417,7 +1362,7 @@ int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc
         SH_LAUNCH("class_adj_prep_kernel", st,
                   class_adj_raw_kernel<<<K * cpc, kAdjWarps * 32, 0, st>>>(edge_weights, b.rowinv, K, Vc, b.ldk, G_BM * gemm_ctas(),
                                                                            class_table_tail(p, K, Vc) ? 0 : 1, remove_self_loop,
-                                                                           b.n_act, b.old_of_new, b.adj_hi, b.adj_lo, cpc));
+                                                                           b.n_act, b.old_of_new, b.adj, cpc));
         SH_CHECK_LAUNCH();
     }
     return class_layers_tc(p, K, Vc, b, chunks, partial, st, fin);

@@ -51,6 +51,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+// same, acquiring at cluster scope: for barriers that CTAs of the cluster arrive on remotely after writing shared memory
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("libschemahead: mbarrier wait (cluster) timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // TMA tiled loads (global -> swizzled shared memory), completion on an mbarrier
 // ---------------------------------------------------------------------------------------------------------------
