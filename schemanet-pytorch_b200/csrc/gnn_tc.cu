@@ -1,31 +1,38 @@
-// gnn_tc.cu -- stage 3b on tcgen05 tensor cores: fp32-accurate "3xTF32" batched GEMMs with fused epilogues.
+// gnn_tc.cu -- stage 3b on tcgen05 tensor cores: fp32-accurate batched GEMMs ("3 x fp16": three kind::f16 MMAs per
+// product) with fused epilogues.
 //
 // Replaces the bmm / Linear / LayerNorm / ReLU chain of GraphConv + Layer (schema_inference/graph/gnn.py:20-46) for
 // embed_dim % 256 == 0, embed_dim <= 1024 (256: everything fused as described below; wider: bias in the GEMM epilogue,
 // LayerNorm + ReLU as a separate pass).  Other widths stay on the fp32 CUDA-core path (gnn.cu).
 //
-// Precision: the north star allows 1e-5 relative error on logits, which plain TF32 (10-bit mantissa) cannot meet.
-// Every fp32 operand x is therefore split as x = hi + lo with hi = x & 0xffffe000 (exactly representable in TF32) and
-// lo = x - hi (exact in fp32, 13 significant bits), and each product is accumulated as
-//       a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi        (three kind::tf32 MMAs into the same fp32 TMEM accumulator)
-// which leaves a relative error of ~2^-21 per product -- the same order as fp32 FMA accumulation itself.
-// Operands live in HBM ONCE, as plain fp32: TMA brings the fp32 tile into the stage's "hi" slot and four transform warps
-// split it in place (hi overwrites the tile, lo goes to the slot next to it; element positions are unchanged, so the
-// 128-byte swizzle TMA applied is preserved) before the MMA warp is released.  Round 1 stored every operand as a hi/lo
-// pair in HBM: twice the bytes on every producer and on every GEMM read, which made the class-side GEMMs HBM kernels.
+// Precision: the north star allows 1e-5 relative error on logits, which a single 16-bit or TF32 pass cannot meet.  Every
+// fp32 operand x is scaled by a power of two s (exact) and split as  s x = hi + lo + r:
+//     hi = (s x) & 0xffffe000   11 significant bits: exactly representable in fp16
+//     lo = fp16_rn(s x - hi)    the next 11 bits;  |r| <= 2^-21 |s x|
+// and each product is accumulated as  a b ~= a_lo b_hi + a_hi b_lo + a_hi b_hi  by three kind::f16 MMAs into one fp32 TMEM
+// accumulator (products of fp16 values are exact in fp32; the dropped a_lo b_lo term is <= 2^-20 |a b|), i.e. the accuracy
+// of the "3xTF32" scheme of round 1 at TWICE the tensor rate and half the shared-memory operand bytes per flop.
+// s = 2^k with max |s x| in [2^14, 2^15): the maximum of every operand tensor is recorded on the device by the kernel that
+// produces it (atomicMax on the bit pattern, `amax` slots in the workspace) and read by the consuming GEMM -- no host
+// round trip, no overflow for any input range, and the epilogue undoes both scales with one exact multiplication.
+//
+// Operands live in HBM ONCE, as plain fp32.  TMA brings the fp32 tiles (32 k-elements x 128 rows, 128-byte swizzle) into a
+// 32 KB stage; four transform warps convert them IN PLACE into four 8 KB fp16 tiles (A hi, A lo, B hi, B lo) in the
+// un-swizzled K-major core-matrix layout (8 rows x 16 bytes contiguous, LBO 128 B, SBO 512 B) and release the MMA warp.
+// Half the bytes per stage of the hi/lo fp32 scheme -> a 6-deep ring instead of 3, which is what hides the TMA latency.
 //
 // Per layer, for a batch of G graphs with n_g <= n_fixed nodes:
 //   adj GEMM     Y[g]  = Adj[g] (n x n, symmetric, K-major)  *  X[g]   given as X^T [D, n] (K-major)   -> Y  [n, D]
 //   linear GEMM  Z     = Y (rows x D, K-major) * W^T with W [D_out, D_in] (K-major), + bias, LayerNorm, ReLU fused in
 //                the TMEM epilogue (one thread owns one full 256-wide row: LayerNorm needs no cross-thread reduction)
-//                -> H^T [D, n] as hi/lo for the next layer's adj GEMM, or H [rows, D] for the pooling.
+//                -> H^T [D, n] for the next layer's adj GEMM, or H [rows, D] for the pooling.
 // Layer 0 is shortened to ONE adjacency GEMM with bias + LayerNorm + ReLU in its epilogue (the first Linear is applied to
 // the (M+1)-row embedding table instead, see run_layers_tc); the last layer's epilogue emits vertex-weighted group sums
 // instead of activations.  Class graphs run on their un-pruned vertices only (class_perm_kernel, per-code tables).
-// Kernel layout: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5 epilogue, warps 6-9 operand transform
-// (fp32 -> hi/lo in shared memory); CTA pairs (cta_group::2, one UMMA of M = 256 per pair, each CTA stages and splits its
-// 128 A rows and half of the B tile) with a 3-stage 64 KB shared-memory ring per CTA, or single CTAs with a 2-stage 96 KB
-// ring (SCHEMANET_GEMM_CTAS=1); 2-stage 256-column TMEM accumulator ring.
+// Kernel layout: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5 epilogue, warps 6-9 operand transform;
+// CTA pairs (cta_group::2, one UMMA of M = 256 per pair, each CTA stages and converts its 128 A rows and half of the B
+// tile), or single CTAs (SCHEMANET_GEMM_CTAS=1, 48 KB stages, 4-deep); 2-stage 256-column TMEM accumulator ring.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "gnn_tc.cuh"
@@ -69,7 +76,27 @@ struct GemmTcArgs {
     int ldk;                     // row stride of the transposed output
     const float *bias, *gamma, *beta;
     float eps;
+    // dynamic operand scaling: bit patterns of max |A|, max |B| (written by the kernels that produced the operands) and the
+    // slot this launch records the maximum of its own output in (null: the output is not a GEMM operand)
+    const unsigned *amax_a, *amax_b;
+    unsigned *amax_out;
 };
+
+// power-of-two scale that puts a tensor whose largest magnitude has the bit pattern `bits` into [2^14, 2^15)
+__device__ __forceinline__ float scale_from_amax(unsigned bits)
+{
+    int e = (int)((bits >> 23) & 0xffu);                 // max < 2^(e - 126)
+    if (bits == 0u) return 1.0f;
+    int k = 141 - e;                                     // 2^k * max < 2^15
+    k = k > 60 ? 60 : k;                                 // (tensors below 2^-45 are not scaled further: no overflow of s_a s_b)
+    return __uint_as_float((unsigned)(127 + k) << 23);
+}
+
+__device__ __forceinline__ void record_amax(unsigned *slot, float m)
+{
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && slot != nullptr && !(m == 0.0f)) atomicMax(slot, __float_as_uint(m));   // NaN compares above +inf
+}
 
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo)
 {
@@ -98,29 +125,59 @@ __device__ __forceinline__ void store_chunk_rows(float *tile /* [32][33] */, con
     }
 }
 
-// In-place operand split of `bytes` of a stage slot (hi overwrites, lo at +lo_off), 16 bytes per thread and step.
-__device__ __forceinline__ void split_region(uint32_t base, uint32_t lo_off, int bytes, int tid, int nthreads)
+// Shared-memory matrix descriptor for the fp16 tiles the transform warps write: K-major, no swizzle ("interleaved"): a core
+// matrix is 8 rows x 16 bytes, contiguous; the two 16-byte k-chunks of one K = 16 step are LBO = 128 bytes apart, 8-row
+// groups SBO = 512 bytes apart (cute::UMMA make_umma_desc<Major::K>, LayoutType::INTERLEAVE; checked on the device by
+// tools/probe/umma_probe.cu).  Chunk (row r, k-chunk c of 4) of a tile sits at (r >> 3) * 512 + c * 128 + (r & 7) * 16.
+__device__ __forceinline__ uint64_t make_desc_k_interleaved(uint32_t smem_addr)
 {
-    for (int o = tid * 16; o < bytes; o += nthreads * 16) {
-        float4 x;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(base + o));
-        float4 h, l;
-        split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(base + o), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(base + o + lo_off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 x;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
+    return x;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// two scaled fp32 values -> packed fp16 pair of their 11-bit heads (exact) and of the rounded remainders
+__device__ __forceinline__ void split_pair(float x0, float x1, float s, uint32_t &hi, uint32_t &lo)
+{
+    x0 *= s; x1 *= s;
+    const float h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
+    const __half2 hh = __floats2half2_rn(h0, h1), ll = __floats2half2_rn(x0 - h0, x1 - h1);
+    hi = *reinterpret_cast<const uint32_t *>(&hh);
+    lo = *reinterpret_cast<const uint32_t *>(&ll);
+}
+// one 128-byte landing row (8 float4, already un-swizzled into k order) -> its 4 hi and 4 lo 16-byte chunks
+__device__ __forceinline__ void convert_row(const float4 (&v)[8], float s, uint32_t hi_base, uint32_t lo_base)
+{
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t h[4], l[4];
+        split_pair(v[2 * c].x, v[2 * c].y, s, h[0], l[0]);
+        split_pair(v[2 * c].z, v[2 * c].w, s, h[1], l[1]);
+        split_pair(v[2 * c + 1].x, v[2 * c + 1].y, s, h[2], l[2]);
+        split_pair(v[2 * c + 1].z, v[2 * c + 1].w, s, h[3], l[3]);
+        sts128(hi_base + c * 128, h[0], h[1], h[2], h[3]);
+        sts128(lo_base + c * 128, l[0], l[1], l[2], l[3]);
     }
 }
 
-// Shared-memory plan.  CTAS == 1: one CTA per 128-row block, stage = hi+lo of A (2 x 16 KB) and of the whole 256-row
-// B tile (2 x 32 KB) = 96 KB, 2 stages.  CTAS == 2 (cta_group::2): a CTA pair computes a 256-row block with one UMMA
-// of M = 256; each CTA stages its own 128 A rows and HALF of the B tile (2 x 16 KB), i.e. 64 KB per stage and a third
-// less L2->SM traffic per flop, which buys a third stage.
+// Shared-memory plan.  A stage is the fp32 landing area of one k-block: 128 A rows (16 KB) + this CTA's B rows (CTA pair:
+// 128 rows, 16 KB; single CTA: 256 rows, 32 KB).  The conversion is in place: each region ends up as [hi tile | lo tile].
 template <int CTAS>
 struct GemmPlan {
     static constexpr int kBRows = G_BN / CTAS;
-    static constexpr int kBBytesL = kBRows * G_BK * 4;
-    static constexpr int kStage = 2 * kABytes + 2 * kBBytesL;
-    static constexpr int kStages = CTAS == 1 ? 2 : 3;
+    static constexpr int kBBytesL = kBRows * G_BK * 4;            // landing bytes of the B rows = hi tile + lo tile
+    static constexpr int kBTile = kBBytesL / 2;
+    static constexpr int kStage = kABytes + kBBytesL;
+    static constexpr int kStages = CTAS == 1 ? 4 : 6;
     static constexpr int kBar = kStages * kStage;
     static constexpr int kParam = kBar + 256;
     static constexpr int kStageOut = kParam + (2 * G_BN + kMaxDim) * 4;   // gamma, beta (LN: 256 wide) + bias (up to kMaxDim)
@@ -138,7 +195,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // the compiler lose the address space and emit 64-bit generic LD/ST for every shared-memory access of the epilogue
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full = (uint64_t *)(smem + P::kBar);       // TMA bytes of this CTA's slot have landed (local)
-    uint64_t *ready = full + S;                          // both CTAs' slots are split into hi/lo (lives in the leader)
+    uint64_t *ready = full + S;                          // both CTAs' slots are converted to fp16 hi/lo (lives in the leader)
     uint64_t *empty = ready + S;
     uint64_t *tmem_full = empty + S;
     uint64_t *tmem_empty = tmem_full + 2;
@@ -148,6 +205,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;     // 0 = the CTA that issues the MMAs
     const int unit = (int)blockIdx.x / CTAS, num_units = (int)gridDim.x / CTAS;
+    const float scale_a = scale_from_amax(__ldg(a.amax_a)), scale_b = scale_from_amax(__ldg(a.amax_b));
+    const float unscale = (1.0f / scale_a) * (1.0f / scale_b);      // powers of two: exact
 
     if (EPI == EPI_LN_RELU_T || EPI == EPI_LN_RELU_ROWS)
         for (int i = threadIdx.x; i < G_BN; i += G_THREADS) { s_bias[i] = a.bias[i]; s_gamma[i] = a.gamma[i]; s_beta[i] = a.beta[i]; }
@@ -206,18 +265,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *s = smem + stage * P::kStage;
                     const int gb = a.batched_b ? g : 0;
-                    // every CTA loads its own fp32 tiles (128 A rows, its share of the B tile) into the hi slots and
-                    // tracks them on its OWN barrier: its transform warps wait there
-                    mbar_arrive_expect_tx(&full[stage], kABytes + P::kBBytesL);
+                    // every CTA loads its own fp32 tiles (128 A rows, its share of the B tile) and tracks them on its OWN
+                    // barrier: its transform warps wait there
+                    mbar_arrive_expect_tx(&full[stage], P::kStage);
                     tma_load_3d(s, &tmA, &full[stage], kb * G_BK, mb * G_BM, g);
-                    tma_load_3d(s + 2 * kABytes, &tmB, &full[stage], kb * G_BK, nb * G_BN + rank * P::kBRows, gb);
+                    tma_load_3d(s + kABytes, &tmB, &full[stage], kb * G_BK, nb * G_BN + rank * P::kBRows, gb);
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             TILE_LOOP_END
         }
     } else if (warp == 1) {
         if (rank == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(G_BM * CTAS, G_BN);
+            constexpr uint32_t idesc = make_idesc_f16(G_BM * CTAS, G_BN);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             TILE_LOOP_BEGIN
@@ -225,23 +284,23 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * G_BN);
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait_cluster(&ready[stage], phase);     // hi/lo of both CTAs' slots are in place
+                    mbar_wait(&ready[stage], phase);             // fp16 hi/lo tiles of both CTAs' slots are in place
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t s = smem_u32(smem + stage * P::kStage);
-                        const uint64_t ah = make_desc_k_sw128(s), al = make_desc_k_sw128(s + kABytes);
-                        const uint64_t bh = make_desc_k_sw128(s + 2 * kABytes), bl = make_desc_k_sw128(s + 2 * kABytes + P::kBBytesL);
+                        const uint64_t ah = make_desc_k_interleaved(s), al = make_desc_k_interleaved(s + kABytes / 2);
+                        const uint64_t bh = make_desc_k_interleaved(s + kABytes), bl = make_desc_k_interleaved(s + kABytes + P::kBTile);
 #pragma unroll
-                        for (int k = 0; k < G_BK / 8; ++k) {
-                            const uint64_t o = (uint64_t)(2 * k);
+                        for (int k = 0; k < G_BK / 16; ++k) {          // one UMMA consumes 16 halves of K: two 16-byte chunks, 256 bytes on
+                            const uint64_t o = (uint64_t)(16 * k);
                             if (CTAS == 1) {
-                                umma_tf32(tmem_d, al + o, bh + o, idesc, (kb | k) != 0);   // small terms first
-                                umma_tf32(tmem_d, ah + o, bl + o, idesc, 1);
-                                umma_tf32(tmem_d, ah + o, bh + o, idesc, 1);
+                                umma_f16(tmem_d, al + o, bh + o, idesc, (kb | k) != 0);   // small terms first
+                                umma_f16(tmem_d, ah + o, bl + o, idesc, 1);
+                                umma_f16(tmem_d, ah + o, bh + o, idesc, 1);
                             } else {
-                                umma_tf32_pair(tmem_d, al + o, bh + o, idesc, (kb | k) != 0);
-                                umma_tf32_pair(tmem_d, ah + o, bl + o, idesc, 1);
-                                umma_tf32_pair(tmem_d, ah + o, bh + o, idesc, 1);
+                                umma_f16_pair(tmem_d, al + o, bh + o, idesc, (kb | k) != 0);
+                                umma_f16_pair(tmem_d, ah + o, bl + o, idesc, 1);
+                                umma_f16_pair(tmem_d, ah + o, bh + o, idesc, 1);
                             }
                         }
                         if (CTAS == 1) {
@@ -268,6 +327,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * G_BN);
             const int m = mb * G_BM + row_in_tile;           // row inside this batch entry
+            float out_max = 0.0f;                            // largest magnitude this thread writes (the next GEMM's operand scale)
             if (EPI == EPI_STORE_ROWS) {
                 // Y[g, m, :] (row-major: the K-major A operand of the linear GEMM)
                 // warp-level view: this warp owns rows [mb*128 + wq*32, +32) of graph g
@@ -278,6 +338,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 for (int c = 0; c < G_BN / 32; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { v[j] *= unscale; out_max = fmaxf(out_max, fabsf(v[j])); }
                     store_chunk_rows(s_out + wq * 32 * 33, v, lane, o + c * 32, a.N_total, rows_valid);
                 }
             } else if (EPI == EPI_BIAS_ROWS) {
@@ -289,7 +351,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += s_bias[nb * G_BN + c * 32 + j];
+                    for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], unscale, s_bias[nb * G_BN + c * 32 + j]);
                     store_chunk_rows(s_out + wq * 32 * 33, v, lane, o + c * 32, a.N_total, min(32, a.M_total - m_warp));
                 }
             } else {
@@ -312,14 +374,14 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            q0 += v[j] + s_bias[j]; q1 += v[j + 1] + s_bias[j + 1];
-                            q2 += v[j + 2] + s_bias[j + 2]; q3 += v[j + 3] + s_bias[j + 3];
+                            q0 += fmaf(v[j], unscale, s_bias[j]); q1 += fmaf(v[j + 1], unscale, s_bias[j + 1]);
+                            q2 += fmaf(v[j + 2], unscale, s_bias[j + 2]); q3 += fmaf(v[j + 3], unscale, s_bias[j + 3]);
                         }
                         shift = ((q0 + q1) + (q2 + q3)) * (1.0f / 32.0f);
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float tt = v[j] + s_bias[c * 32 + j] - shift;
+                        const float tt = fmaf(v[j], unscale, s_bias[c * 32 + j]) - shift;
                         p1[j & 3] += tt;
                         p2[j & 3] = fmaf(tt, tt, p2[j & 3]);
                     }
@@ -336,7 +398,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = c * 32 + j;
-                        const float z = v[j] + s_bias[n];
+                        const float z = fmaf(v[j], unscale, s_bias[n]);
                         v[j] = fmaxf((z - mean) * rstd * s_gamma[n] + s_beta[n], 0.0f);
                     }
                     if (EPI == EPI_LN_RELU_ROWS && a.pool_groups != nullptr) {
@@ -384,11 +446,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
                             for (int j = 0; j < 32; ++j) o[(size_t)j * a.ldk] = valid ? v[j] : 0.0f;
                         }
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) out_max = fmaxf(out_max, v[j]);      // (after ReLU: v >= 0)
+                        }
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
+            if (EPI == EPI_STORE_ROWS || EPI == EPI_LN_RELU_T) record_amax(a.amax_out, out_max);
             if (lane == 0) {
                 if (CTAS == 1) mbar_arrive(&tmem_empty[as]);
                 else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));   // the leader owns the accumulator ring
@@ -396,9 +463,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (++as == 2) { as = 0; aphase ^= 1; }
         TILE_LOOP_END
     } else {
-        // ===================== operand transform: fp32 tile -> hi / lo, in place =====================
+        // ===================== operand transform: fp32 landing tiles -> fp16 hi / lo tiles, in place =====================
+        // Thread t owns landing row t of A and rows t (+128) of B: it reads the whole 128-byte rows (the 16-byte chunk c
+        // of row r was stored by TMA at position c ^ (r & 7); a quarter-warp touches 8 rows = 8 distinct chunk positions:
+        // no bank conflicts), waits until all 128 transform threads have read (the fp16 tiles overwrite other threads'
+        // landing rows), then writes its 4 + 4 chunks per row (a quarter-warp writes one contiguous 128-byte core matrix).
         const int tid = (int)threadIdx.x - 6 * 32;                  // 0 .. 127
         const uint32_t ready_lead = mapa_u32(smem_u32(&ready[0]), 0);
+        const uint32_t swz = (uint32_t)(tid & 7);
+        const uint32_t row_off = (uint32_t)((tid >> 3) * 512 + (tid & 7) * 16);    // of row t inside an fp16 tile
+        constexpr int kBPer = P::kBRows / 128;                      // B rows per thread
         int stage = 0;
         uint32_t phase = 0;
         TILE_LOOP_BEGIN
@@ -406,12 +480,24 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             for (int kidx = 0; kidx < kblocks; ++kidx) {
                 mbar_wait(&full[stage], phase);                     // this CTA's fp32 tiles have landed
                 const uint32_t sb = smem_u32(smem + stage * P::kStage);
-                split_region(sb, kABytes, kABytes, tid, 128);
-                split_region(sb + 2 * kABytes, P::kBBytesL, P::kBBytesL, tid, 128);
+                float4 va[8], vb[kBPer][8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) va[c] = lds128(sb + (uint32_t)tid * 128u + (((uint32_t)c ^ swz) << 4));
+#pragma unroll
+                for (int h = 0; h < kBPer; ++h)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        vb[h][c] = lds128(sb + kABytes + (uint32_t)(tid + 128 * h) * 128u + (((uint32_t)c ^ swz) << 4));
+                asm volatile("bar.sync 2, 128;" ::: "memory");       // every landing row is in registers
+                convert_row(va, scale_a, sb + row_off, sb + kABytes / 2 + row_off);
+#pragma unroll
+                for (int h = 0; h < kBPer; ++h)
+                    convert_row(vb[h], scale_b, sb + kABytes + row_off + (uint32_t)(h * 16 * 512),
+                                sb + kABytes + P::kBTile + row_off + (uint32_t)(h * 16 * 512));
                 fence_proxy_async();                                // generic-proxy stores -> visible to the UMMA (async proxy)
                 __syncwarp();
                 if (lane == 0) {
-                    if (CTAS == 1) mbar_arrive(&ready[stage]);
+                    if (rank == 0) mbar_arrive(&ready[stage]);
                     else mbar_arrive_cluster(ready_lead + (uint32_t)(stage * 8));
                 }
                 if (++stage == S) { stage = 0; phase ^= 1; }
@@ -433,9 +519,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // goes through shared memory so that both reads are coalesced.
 __global__ void __launch_bounds__(256)
 adj_prep_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int32_t *__restrict__ sizes, int n_fixed,
-                int ldk, float *__restrict__ adj)
+                int ldk, float *__restrict__ adj, unsigned *amax)
 {
     __shared__ float tile[32][33];
+    float mx = 0.0f;
     const int g = blockIdx.z;
     const int n_g = sizes ? sizes[g] : n_fixed;
     const int ld = e_ld > 0 ? e_ld : n_g;
@@ -453,8 +540,10 @@ adj_prep_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const in
             float v = 0.0f;
             if (i < n_g && j < n_g) v = (Eg[(size_t)i * ld + j] + tile[tx][r]) / 2.0f + (i == j ? 1.0f : 0.0f);
             adj[((size_t)g * n_fixed + i) * ldk + j] = v;
+            mx = fmaxf(mx, fabsf(v));
         }
     }
+    record_amax(amax, mx);
 }
 
 // Same result as adj_prep_kernel with the work organised like class_adj_raw_kernel below: (E + E^T) / 2 is symmetric,
@@ -473,9 +562,10 @@ __device__ __forceinline__ void adj_zero_strip(float *__restrict__ adj, size_t b
 
 __global__ void __launch_bounds__(128)
 adj_sym_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int32_t *__restrict__ sizes, int n_fixed, int ldk,
-               float *__restrict__ adj, int ctas_per_graph)
+               float *__restrict__ adj, int ctas_per_graph, unsigned *amax)
 {
     __shared__ float tiles[4][2][32][33];
+    float mx = 0.0f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x / ctas_per_graph;
     const int wid = (blockIdx.x % ctas_per_graph) * 4 + warp, nw = ctas_per_graph * 4;
@@ -525,6 +615,7 @@ adj_sym_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int
                 float sym = 0.0f;
                 if (r < nvi && vj) sym = (v[u] + T[lane][r]) / 2.0f + ((r == diag) ? 1.0f : 0.0f);
                 S[r][lane] = sym;
+                mx = fmaxf(mx, fabsf(sym));
                 if (col_ok && i0 + r < n_fixed) *ph = sym;
                 ph += ldk;
             }
@@ -541,6 +632,7 @@ adj_sym_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int
         }
         __syncwarp();
     }
+    record_amax(amax, mx);
 }
 
 // X0^T[g, d, i] = Emb[ids[g, i], d] (gnn.py:91), zero for i >= n_g.  One CTA per (32 nodes, 256 features, graph):
@@ -548,7 +640,7 @@ adj_sym_kernel(const float *__restrict__ E, int64_t e_batch, int e_ld, const int
 // shared memory and written as 128-byte row segments of X^T.
 __global__ void __launch_bounds__(256)
 embed_gather_t_kernel(const float *__restrict__ emb, const int64_t *__restrict__ ids, int ld_ids,
-                      const int32_t *__restrict__ sizes, int n_fixed, int ldk, int D, float *__restrict__ xt)
+                      const int32_t *__restrict__ sizes, int n_fixed, int ldk, int D, float *__restrict__ xt, unsigned *amax)
 {
     __shared__ float tile[32][257];
     const int g = blockIdx.z;
@@ -566,9 +658,14 @@ embed_gather_t_kernel(const float *__restrict__ emb, const int64_t *__restrict__
     }
     __syncthreads();
     const int i = i0 + lane;
-    if (i >= ldk) return;
-    for (int d = warp; d < dn; d += 8)                 // feature d0 + d, nodes i0 .. i0 + 31 (coalesced along i)
-        xt[((size_t)g * D + d0 + d) * ldk + i] = tile[lane][d];
+    float mx = 0.0f;
+    if (i < ldk)
+        for (int d = warp; d < dn; d += 8) {           // feature d0 + d, nodes i0 .. i0 + 31 (coalesced along i)
+            const float v = tile[lane][d];
+            xt[((size_t)g * D + d0 + d) * ldk + i] = v;
+            mx = fmaxf(mx, fabsf(v));
+        }
+    record_amax(amax, mx);
 }
 
 constexpr int kTableSlices = 8;   // CTAs per class summing the pruned vertices' table rows (pool_table_rows_kernel)
@@ -753,7 +850,8 @@ class_perm_kernel(const float *__restrict__ cv, const int64_t *__restrict__ ci, 
 // up to the tile edges) and the 128x128 diagonal blocks of row blocks that contain inactive vertices.
 __global__ void __launch_bounds__(256)
 class_adj_prep_kernel(const float *__restrict__ ce, int K, int Vc, int ldk, int unit_rows, int with_tail,
-                      const int32_t *__restrict__ n_act, const int32_t *__restrict__ old_of_new, float *__restrict__ adj)
+                      const int32_t *__restrict__ n_act, const int32_t *__restrict__ old_of_new, float *__restrict__ adj,
+                      unsigned *amax)
 {
     // One CTA per 32x32 tile; tiles outside the regions the GEMM reads exit at once.  (A persistent variant that walked
     // the tile space with two block barriers per tile measured 45 % slower.)
@@ -769,6 +867,7 @@ class_adj_prep_kernel(const float *__restrict__ ce, int K, int Vc, int ldk, int 
         const bool in_a = pi0 < rowsA && pj0 < colsA;
         const bool in_b = with_tail && (ub + 1) * unit_rows > nA && pj0 / unit_rows == ub;
         if (!in_a && !in_b) return;
+        float mx = 0.0f;
         const float *cek = ce + (size_t)k * Vc * Vc;
         const int32_t *old = old_of_new + (size_t)k * Vc;
         const bool any_active = pi0 < nA && pj0 < nA;
@@ -800,8 +899,10 @@ class_adj_prep_kernel(const float *__restrict__ ce, int K, int Vc, int ldk, int 
                 float v = (pi == pj) ? 1.0f : 0.0f;
                 if (any_active && pi < nA && pj < nA) v = (direct[u] + tile[tx][r]) / 2.0f + v;
                 adj[((size_t)k * Vc + pi) * ldk + pj] = v;
+                mx = fmaxf(mx, fabsf(v));
             }
         }
+        record_amax(amax, mx);
     }
 }
 
@@ -835,9 +936,10 @@ __device__ __forceinline__ void adj_fill_strip(float *__restrict__ adj, size_t b
 __global__ void __launch_bounds__(kAdjWarps * 32)
 class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ rowinv, int K, int Vc, int ldk, int unit_rows,
                      int with_tail, int remove_self_loop, const int32_t *__restrict__ n_act,
-                     const int32_t *__restrict__ old_of_new, float *__restrict__ adj, int ctas_per_class)
+                     const int32_t *__restrict__ old_of_new, float *__restrict__ adj, int ctas_per_class, unsigned *amax)
 {
     __shared__ float tiles[kAdjWarps][2][32][33];
+    float mx = 1.0f;                      // (the identity / padding strips hold ones)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // last classes first: their edge parameters are what the atlas pass, which ran just before, left in L2
     const int k = K - 1 - blockIdx.x / ctas_per_class;
@@ -915,6 +1017,7 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
                 if (remove_self_loop && __shfl_sync(kFull, oi, r) == oj) e = 0.0f;
                 const float sym = (e + T[lane][r]) / 2.0f + ((r == diag) ? 1.0f : 0.0f);
                 S[r][lane] = sym;
+                mx = fmaxf(mx, fabsf(sym));
                 if (col_ok && pi0 + r < Vc) *ph = sym;
                 ph += ldk;
             }
@@ -931,6 +1034,20 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
         }
         __syncwarp();
     }
+    record_amax(amax, mx);
+}
+
+// largest magnitude of each layer's Linear weight matrix (the B operand of the linear GEMMs): one CTA per layer
+struct WeightPtrs { const float *w[16]; };
+__global__ void __launch_bounds__(256) weights_absmax_kernel(WeightPtrs p, int n, unsigned *amax)
+{
+    const float4 *w = reinterpret_cast<const float4 *>(p.w[blockIdx.y]);
+    float mx = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += gridDim.x * blockDim.x) {
+        const float4 v = __ldg(w + i);
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    record_amax(amax + blockIdx.y, mx);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -943,7 +1060,8 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
 template <bool kTranspose>
 __global__ void __launch_bounds__(256)
 ln_relu_wide_kernel(float *__restrict__ Z, const int32_t *__restrict__ row_sizes, int n_fixed, int ldk, int D,
-                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float *__restrict__ xt)
+                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float *__restrict__ xt,
+                    unsigned *amax)
 {
     extern __shared__ float slab[];   // kTranspose: [32][D + 1]
     const int g = blockIdx.y, i0 = blockIdx.x * 32;
@@ -971,9 +1089,14 @@ ln_relu_wide_kernel(float *__restrict__ Z, const int32_t *__restrict__ row_sizes
     if (kTranspose) {
         __syncthreads();
         const int i = i0 + lane;
+        float mx = 0.0f;
         if (i < ldk)
-            for (int dd = warp; dd < D; dd += 8)
-                xt[((size_t)g * D + dd) * ldk + i] = i < n_fixed ? slab[lane * (D + 1) + dd] : 0.0f;
+            for (int dd = warp; dd < D; dd += 8) {
+                const float v = i < n_fixed ? slab[lane * (D + 1) + dd] : 0.0f;
+                xt[((size_t)g * D + dd) * ldk + i] = v;
+                mx = fmaxf(mx, v);
+            }
+        record_amax(amax, mx);
     }
 }
 
@@ -986,6 +1109,7 @@ bool gnn_tc_supported(int D, int n_fixed)
 
 struct TcBuffers {
     float *adj, *xt, *xt2, *y, *tab, *h_rows;     // tab: (M+1)-row table scratch (P_0 = Emb W_0^T), same size as y
+    unsigned *amax;                               // operand maxima (bit patterns), see AM_* below; zeroed per forward
     int32_t *n_act, *old_of_new;
     float *rowinv, *pool_extra, *pool_groups;
     int64_t *pid;
@@ -1015,6 +1139,7 @@ static TcBuffers carve_tc(void *base, int G, int n_fixed, int D)
     b.pool_groups = (float *)(p + off); off += al256(((size_t)G * n_fixed / 32 + 2) * 2 * D * 4);
     b.pid = (int64_t *)(p + off); off += al256((size_t)G * n_fixed * 8);
     b.pvw = (float *)(p + off); off += al256((size_t)G * n_fixed * 4);
+    b.amax = (unsigned *)(p + off); off += 256;
     b.bytes = off;
     return b;
 }
@@ -1024,6 +1149,11 @@ size_t gnn_tc_workspace_bytes(int G, int n_fixed, int D, int chunks)
     (void)chunks;
     return carve_tc(nullptr, G, n_fixed, D).bytes + 4096;
 }
+
+// amax slots: the adjacency, the Linear weights of layer l, the node features entering layer l (l = num_layers: never
+// consumed), the adjacency product Y of layer l
+constexpr int kMaxTcLayers = 16;
+constexpr int AM_ADJ = 0, AM_W = 1, AM_X = 1 + kMaxTcLayers, AM_Y = 2 + 2 * kMaxTcLayers;     // 64 slots in all
 
 static int gemm_ctas()
 {
@@ -1129,6 +1259,16 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
                         const float *vertex_w, const TcBuffers &b, cudaStream_t st, bool table_tail)
 {
     const int D = p->embed_dim;
+    SH_REQUIRE(p->num_layers <= kMaxTcLayers, "gnn: at most %d layers on the tensor-core path", kMaxTcLayers);
+    // operand maxima of this forward: reset, then the Linear weights' (every other slot is written by the kernel that
+    // produces the operand)
+    SH_CHECK_CUDA(cudaMemsetAsync(b.amax, 0, 256, st));
+    {
+        WeightPtrs wp{};
+        for (int l = 0; l < p->num_layers; ++l) wp.w[l] = p->lin_w[l];
+        SH_LAUNCH("gnn_weights_absmax", st, weights_absmax_kernel<<<dim3(16, p->num_layers), 256, 0, st>>>(wp, D * D, b.amax + AM_W));
+        SH_CHECK_LAUNCH();
+    }
     if (!layer0_fused(p, G, n_fixed)) return 0;
     static const bool serial = getenv("SCHEMANET_TABLES_INLINE") != nullptr;
     AuxLane *lane = (serial || prof_on()) ? nullptr : aux_lane(table_tail ? 1 : 0);   // profiling: a kernel's time is its own
@@ -1158,7 +1298,7 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
         // X_0^T of the fused layer 0 (rows of P_0 gathered by node id): L2-write bound, it also runs under the HBM-read-bound
         // operand preparation
         dim3 grid2(ceil_div(b.ldk, 32), ceil_div(D, 256), G);
-        SH_LAUNCH("gnn_embed_gather", ts, embed_gather_t_kernel<<<grid2, 256, 0, ts>>>(b.tab, ids, ld_ids, row_sizes, n_fixed, b.ldk, D, b.xt));
+        SH_LAUNCH("gnn_embed_gather", ts, embed_gather_t_kernel<<<grid2, 256, 0, ts>>>(b.tab, ids, ld_ids, row_sizes, n_fixed, b.ldk, D, b.xt, b.amax + AM_X));
         SH_CHECK_LAUNCH();
     }
     if (lane) SH_CHECK_CUDA(cudaEventRecord(lane->join, ts));
@@ -1191,7 +1331,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     if (tables_join(p, G, n_fixed, st, table_tail)) return 1;
     if (!fuse0) {      // (fused layer 0: already gathered from P_0 by tables_begin)
         dim3 grid2(ceil_div(ldk, 32), ceil_div(D, 256), G);
-        SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(table, ids, ld_ids, row_sizes, n_fixed, ldk, D, b.xt));
+        SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(table, ids, ld_ids, row_sizes, n_fixed, ldk, D, b.xt, b.amax + AM_X));
         SH_CHECK_LAUNCH();
     }
     CUtensorMap adjm, ym;
@@ -1211,18 +1351,19 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
         GemmTcArgs a{};
         a.G = G; a.rows_per_graph = n_fixed; a.M_total = n_fixed; a.K_total = n_fixed; a.N_total = D;
         a.k_sizes = k_sizes; a.identity_tail = identity_tail; a.batched_b = 1; a.skip_masked = table_tail ? 1 : 0;
+        a.amax_a = b.amax + AM_ADJ; a.amax_b = b.amax + AM_X + l;
         if (l == 0 && fuse0) {
             // H1 = relu(LN(Adj (X0 W0^T) + b0)) in one kernel
             a.row_sizes = row_sizes;
             a.bias = p->lin_b[0]; a.gamma = p->ln_w[0]; a.beta = p->ln_b[0]; a.eps = p->ln_eps;
-            a.out_t = xout; a.ldk = ldk; a.out_rows = b.h_rows;
+            a.out_t = xout; a.ldk = ldk; a.out_rows = b.h_rows; a.amax_out = b.amax + AM_X + l + 1;
             if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
             else { if (launch_gemm3x<EPI_LN_RELU_T>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
             float *t = xin; xin = xout; xout = t;
             continue;
         }
         // Y = Adj X
-        a.out_rows = b.y;
+        a.out_rows = b.y; a.amax_out = b.amax + AM_Y + l;
         if (launch_gemm3x<EPI_STORE_ROWS>(m1, m1p, a, "gnn_adj_gemm_tc", st)) return 1;
         // H = relu(LN(Y W^T + b)); the weight matrix is read where it lies (split in shared memory like every operand)
         SH_REQUIRE(((uintptr_t)p->lin_w[l] & 15) == 0, "gnn: Linear weights must be 16-byte aligned for TMA");
@@ -1234,6 +1375,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
         c.skip_masked = table_tail ? 1 : 0;
         c.bias = p->lin_b[l]; c.gamma = p->ln_w[l]; c.beta = p->ln_b[l]; c.eps = p->ln_eps;
         c.out_t = xin; c.ldk = ldk; c.out_rows = b.h_rows;
+        c.amax_a = b.amax + AM_Y + l; c.amax_b = b.amax + AM_W + l; c.amax_out = b.amax + AM_X + l + 1;
         CUtensorMap m2[2] = {ym, wm};
         CUtensorMap m2p[2] = {ym, wm2};
         if (D == G_BN) {
@@ -1250,7 +1392,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
             dim3 grid(ceil_div(ldk, 32), G);
             if (last) {
                 SH_LAUNCH("gnn_ln_relu_wide", st, ln_relu_wide_kernel<false><<<grid, 256, 0, st>>>(b.h_rows, row_sizes, n_fixed, ldk, D, p->ln_w[l],
-                                                                                                  p->ln_b[l], p->ln_eps, nullptr));
+                                                                                                  p->ln_b[l], p->ln_eps, nullptr, nullptr));
             } else {
                 const size_t smem = (size_t)32 * (D + 1) * sizeof(float);
                 static bool configured = false;
@@ -1259,7 +1401,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
                     configured = true;
                 }
                 SH_LAUNCH("gnn_ln_relu_wide", st, ln_relu_wide_kernel<true><<<grid, 256, smem, st>>>(b.h_rows, row_sizes, n_fixed, ldk, D, p->ln_w[l],
-                                                                                                    p->ln_b[l], p->ln_eps, xin));
+                                                                                                    p->ln_b[l], p->ln_eps, xin, b.amax + AM_X + l + 1));
             }
             SH_CHECK_LAUNCH();
         }
@@ -1289,11 +1431,11 @@ int gnn_forward_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *si
     if (tables_begin(p, G, n_fixed, sizes, ids, ld_v, vertex_w, b, st, false)) return 1;
     if (getenv("SCHEMANET_ADJ_TILED") != nullptr) {
         dim3 grid(ceil_div(b.ldk, 32), ceil_div(n_fixed, 32), G);
-        SH_LAUNCH("gnn_adj_prep", st, adj_prep_kernel<<<grid, 256, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj));
+        SH_LAUNCH("gnn_adj_prep", st, adj_prep_kernel<<<grid, 256, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj, b.amax + AM_ADJ));
     } else {
         const int tr = ceil_div(n_fixed, 32);
         const int cpg = max(1, min(16, ceil_div(tr * (tr + 1) / 2 + tr, 4 * 4)));   // ~4 items per warp at full size
-        SH_LAUNCH("gnn_adj_prep", st, adj_sym_kernel<<<G * cpg, 128, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj, cpg));
+        SH_LAUNCH("gnn_adj_prep", st, adj_sym_kernel<<<G * cpg, 128, 0, st>>>(edges, edge_batch_stride, edge_ld, sizes, n_fixed, b.ldk, b.adj, cpg, b.amax + AM_ADJ));
     }
     SH_CHECK_LAUNCH();
     return run_layers_tc(p, G, n_fixed, sizes, 0, sizes, ids, ld_v, vertex_w, ld_v, b, chunks, partial, st, false, fin);
@@ -1328,7 +1470,7 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
     SH_LAUNCH("class_adj_prep_kernel", st,
               class_adj_prep_kernel<<<dim3(ceil_div(b.ldk, 32), ceil_div(Vc, 32), K), 256, 0, st>>>(
                   class_edges, K, Vc, b.ldk, G_BM * gemm_ctas(), class_table_tail(p, K, Vc) ? 0 : 1, b.n_act, b.old_of_new,
-                  b.adj));
+                  b.adj, b.amax + AM_ADJ));
     SH_CHECK_LAUNCH();
     return class_layers_tc(p, K, Vc, b, chunks, partial, st, fin);
 }
@@ -1362,7 +1504,7 @@ int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc
         SH_LAUNCH("class_adj_prep_kernel", st,
                   class_adj_raw_kernel<<<K * cpc, kAdjWarps * 32, 0, st>>>(edge_weights, b.rowinv, K, Vc, b.ldk, G_BM * gemm_ctas(),
                                                                            class_table_tail(p, K, Vc) ? 0 : 1, remove_self_loop,
-                                                                           b.n_act, b.old_of_new, b.adj, cpc));
+                                                                           b.n_act, b.old_of_new, b.adj, cpc, b.amax + AM_ADJ));
         SH_CHECK_LAUNCH();
     }
     return class_layers_tc(p, K, Vc, b, chunks, partial, st, fin);
