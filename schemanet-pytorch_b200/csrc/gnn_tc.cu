@@ -80,6 +80,7 @@ struct GemmTcArgs {
     // slot this launch records the maximum of its own output in (null: the output is not a GEMM operand)
     const unsigned *amax_a, *amax_b;
     unsigned *amax_out;
+    int debug;      // timing experiments (SCHEMANET_GEMM_DEBUG): 1 transform skips its work, 2 no MMAs, 4 epilogue skips its work
 };
 
 // power-of-two scale that puts a tensor whose largest magnitude has the bit pattern `bits` into [2^14, 2^15)
@@ -291,7 +292,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         const uint64_t ah = make_desc_k_interleaved(s), al = make_desc_k_interleaved(s + kABytes / 2);
                         const uint64_t bh = make_desc_k_interleaved(s + kABytes), bl = make_desc_k_interleaved(s + kABytes + P::kBTile);
 #pragma unroll
-                        for (int k = 0; k < G_BK / 16; ++k) {          // one UMMA consumes 16 halves of K: two 16-byte chunks, 256 bytes on
+                        for (int k = 0; k < ((a.debug & 2) ? 0 : G_BK / 16); ++k) {          // one UMMA consumes 16 halves of K: two 16-byte chunks, 256 bytes on
                             const uint64_t o = (uint64_t)(16 * k);
                             if (CTAS == 1) {
                                 umma_f16(tmem_d, al + o, bh + o, idesc, (kb | k) != 0);   // small terms first
@@ -328,7 +329,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * G_BN);
             const int m = mb * G_BM + row_in_tile;           // row inside this batch entry
             float out_max = 0.0f;                            // largest magnitude this thread writes (the next GEMM's operand scale)
-            if (EPI == EPI_STORE_ROWS) {
+            if (a.debug & 4) {
+            } else if (EPI == EPI_STORE_ROWS) {
                 // Y[g, m, :] (row-major: the K-major A operand of the linear GEMM)
                 // warp-level view: this warp owns rows [mb*128 + wq*32, +32) of graph g
                 const int m_warp = mb * G_BM + wq * 32;
@@ -489,11 +491,13 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     for (int c = 0; c < 8; ++c)
                         vb[h][c] = lds128(sb + kABytes + (uint32_t)(tid + 128 * h) * 128u + (((uint32_t)c ^ swz) << 4));
                 asm volatile("bar.sync 2, 128;" ::: "memory");       // every landing row is in registers
-                convert_row(va, scale_a, sb + row_off, sb + kABytes / 2 + row_off);
+                if (!(a.debug & 1)) {
+                    convert_row(va, scale_a, sb + row_off, sb + kABytes / 2 + row_off);
 #pragma unroll
-                for (int h = 0; h < kBPer; ++h)
-                    convert_row(vb[h], scale_b, sb + kABytes + row_off + (uint32_t)(h * 16 * 512),
-                                sb + kABytes + P::kBTile + row_off + (uint32_t)(h * 16 * 512));
+                    for (int h = 0; h < kBPer; ++h)
+                        convert_row(vb[h], scale_b, sb + kABytes + row_off + (uint32_t)(h * 16 * 512),
+                                    sb + kABytes + P::kBTile + row_off + (uint32_t)(h * 16 * 512));
+                }
                 fence_proxy_async();                                // generic-proxy stores -> visible to the UMMA (async proxy)
                 __syncwarp();
                 if (lane == 0) {
@@ -933,17 +937,15 @@ __device__ __forceinline__ void adj_fill_strip(float *__restrict__ adj, size_t b
     }
 }
 
-__global__ void __launch_bounds__(kAdjWarps * 32)
-class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ rowinv, int K, int Vc, int ldk, int unit_rows,
-                     int with_tail, int remove_self_loop, const int32_t *__restrict__ n_act,
-                     const int32_t *__restrict__ old_of_new, float *__restrict__ adj, int ctas_per_class, unsigned *amax)
+// The work list of class k (tile pairs of the active corner, then the padding strips) walked by worker `wid` of `nw` warps;
+// T, S: two 32 x 33 shared-memory tiles owned by this warp.  Returns the largest magnitude it wrote.
+__device__ __forceinline__ float class_adj_items(const float *__restrict__ ew, const float *__restrict__ rowinv, int k, int Vc, int ldk,
+                                                 int unit_rows, int with_tail, int remove_self_loop,
+                                                 const int32_t *__restrict__ n_act, const int32_t *__restrict__ old_of_new,
+                                                 float *__restrict__ adj, int wid, int nw, float (*T)[33], float (*S)[33])
 {
-    __shared__ float tiles[kAdjWarps][2][32][33];
+    const int lane = threadIdx.x & 31;
     float mx = 1.0f;                      // (the identity / padding strips hold ones)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // last classes first: their edge parameters are what the atlas pass, which ran just before, left in L2
-    const int k = K - 1 - blockIdx.x / ctas_per_class;
-    const int wid = (blockIdx.x % ctas_per_class) * kAdjWarps + warp, nw = ctas_per_class * kAdjWarps;
     const int nA = n_act[k];
     const int rowsA = min(Vc, (nA + unit_rows - 1) / unit_rows * unit_rows), colsA = (nA + G_BK - 1) / G_BK * G_BK;
     const int nt = (nA + 31) / 32, pairs = nt * (nt + 1) / 2;
@@ -952,8 +954,6 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
     const float *ewk = ew + (size_t)k * Vc * Vc;
     const float *rik = rowinv + (size_t)k * Vc;
     const int32_t *old = old_of_new + (size_t)k * Vc;
-    float (*T)[33] = tiles[warp][0];
-    float (*S)[33] = tiles[warp][1];
     // work list of the class: tile pairs of the active corner first (the expensive items), then one item per 32-row strip
     // of padding
     for (int item = wid; item < pairs + TR; item += nw) {
@@ -1034,6 +1034,21 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
         }
         __syncwarp();
     }
+    return mx;
+}
+
+__global__ void __launch_bounds__(kAdjWarps * 32)
+class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ rowinv, int K, int Vc, int ldk, int unit_rows,
+                     int with_tail, int remove_self_loop, const int32_t *__restrict__ n_act,
+                     const int32_t *__restrict__ old_of_new, float *__restrict__ adj, int ctas_per_class, unsigned *amax)
+{
+    __shared__ float tiles[kAdjWarps][2][32][33];
+    const int warp = threadIdx.x >> 5;
+    // last classes first: their edge parameters are what the atlas pass, which ran just before, left in L2
+    const int k = K - 1 - blockIdx.x / ctas_per_class;
+    const int wid = (blockIdx.x % ctas_per_class) * kAdjWarps + warp, nw = ctas_per_class * kAdjWarps;
+    const float mx = class_adj_items(ew, rowinv, k, Vc, ldk, unit_rows, with_tail, remove_self_loop, n_act, old_of_new, adj, wid, nw,
+                                     tiles[warp][0], tiles[warp][1]);
     record_amax(amax, mx);
 }
 
@@ -1176,6 +1191,9 @@ static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const c
     }
     const int units = a.G * ceil_div(a.M_total, G_BM * CTAS) * (a.N_total / G_BN);
     const int num_units = min(units, sm_count() / CTAS);
+    static const int dbg = [] { const char *e = getenv("SCHEMANET_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+    GemmTcArgs a2 = a;
+    a2.debug = dbg;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(num_units * CTAS);
     cfg.blockDim = dim3(G_THREADS);
@@ -1189,7 +1207,7 @@ static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const c
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     prof_begin(name, st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm3x_kernel<EPI, CTAS>, maps[0], maps[1], a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm3x_kernel<EPI, CTAS>, maps[0], maps[1], a2);
     prof_end(st);
     if (e != cudaSuccess) { set_error("%s launch -> %s", name, cudaGetErrorString(e)); return 1; }
     SH_CHECK_LAUNCH();
@@ -1491,6 +1509,10 @@ int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc
                                                     b.old_of_new, b.pid, b.pvw));
     SH_CHECK_LAUNCH();
     if (tables_begin(p, K, Vc, b.n_act, b.pid, Vc, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;
+    // (Measured and not kept, r02: ONE kernel with a cluster of 4 / 8 CTAs per class -- normalisers in phase 1, cluster barrier,
+    // adjacency gathered from L2 in phase 2.  189-203 us against 90 + 77 us for the two kernels below: a class only gets its
+    // cluster's share of the HBM bandwidth, HBM idles during phase 2, and 18-37 classes in flight leave the latency-bound gather
+    // with a third of the warps.  profiles/r02_experiments.md)
     if (launch_class_edges(edge_weights, class_vertices, K, Vc, prune_threshold, prune_in_place, remove_self_loop, class_edges,
                            b.rowinv, st))
         return 1;
