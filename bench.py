@@ -558,7 +558,8 @@ def run_gpu_arm(args):
         t_dom = fam_ms[dom] * 1e-3 / args.steps          # seconds per step spent in the family
         fam_launches = sum(v["launches"] for k, v in kern.items() if FAMILY.get(k, k) == dom) / args.steps
         tensor_path = any(k.endswith("_tc") for k in kern)
-        tf32_sus, tf32_burst = peaks["bf16_tflops_sustained"] / 2, peaks["bf16_tflops"] / 2
+        # the GNN GEMMs issue kind::f16 MMAs (three per fp32 product): their pipe peak is the measured 16-bit dense rate
+        f16_sus, f16_burst = peaks["bf16_tflops_sustained"], peaks["bf16_tflops"]
         n_act = (head.atlas["class_vertices"] > 0.001).sum(1).tolist()
         visited = visited_gemm_flops(c, n_act, n_inst) if tensor_path else None
 
@@ -573,18 +574,19 @@ def run_gpu_arm(args):
         if dom in ("adjacency_gemm", "linear_gemm") and visited is not None:
             # `achieved` = fp32 multiply-adds (x2) of the tiles the kernel VISITS under the flags it is launched with (same
             # rule as TILE_LOOP in gnn_tc.cu, restated in adj_gemm_kblocks) / the family's summed duration.  Each product
-            # costs the tensor pipe 3 TF32 MMAs, so tensor-pipe use = 3 x frac.
+            # costs the tensor pipe 3 fp16 MMAs, so tensor-pipe use = 3 x frac.
             ach = visited[dom] / t_dom / 1e12
             t_ncu = ncu_of("gemm3x_kernel")
             roof = {"kernel": "gemm3x_kernel (%s: %s)" % (dom, ", ".join(k for k in kern if FAMILY.get(k) == dom)),
-                    "bound": "tensor", "achieved": ach, "peak": tf32_sus, "unit": "TFLOP/s", "frac": ach / tf32_sus,
-                    "frac_vs_burst": ach / tf32_burst, "launches_per_step": fam_launches,
+                    "bound": "tensor", "achieved": ach, "peak": f16_sus, "unit": "TFLOP/s", "frac": ach / f16_sus,
+                    "frac_vs_burst": ach / f16_burst, "launches_per_step": fam_launches,
                     "algorithmic_flops_per_step": visited[dom],
                     "traffic": t_ncu["dram_bytes_per_launch"] if t_ncu else None, "traffic_source": traffic_src,
-                    "peak_source": peaks["source"] + " bf16 sustained / 2 (TF32); frac_vs_burst uses bf16 burst / 2",
-                    "tensor_pipe_frac": 3 * ach / tf32_sus,
-                    "note": "3xTF32 on tcgen05: `achieved` counts each fp32 multiply-add of the visited tiles once; the tensor "
-                            "cores execute 3 TF32 MMAs per product (tensor_pipe_frac = 3 x frac), so frac <= 1/3 by construction"}
+                    "peak_source": peaks["source"] + " bf16 sustained (kind::f16 MMAs run at the 16-bit rate); frac_vs_burst uses bf16 burst",
+                    "tensor_pipe_frac": 3 * ach / f16_sus,
+                    "note": "fp32-accurate GEMM as 3 fp16 MMAs per product on tcgen05: `achieved` counts each fp32 multiply-add of the "
+                            "visited tiles once; the tensor cores execute 3 MMAs per product (tensor_pipe_frac = 3 x frac), so "
+                            "frac <= 1/3 by construction"}
         elif dom == "discretize":
             ach = alg["discretize"]["flops"] / t_dom / 1e12
             peak = peaks["bf16_tflops_sustained"]
@@ -627,7 +629,7 @@ def run_gpu_arm(args):
             t = stage_ms[STAGE_3B] * 1e-3
             fl = visited["adjacency_gemm"] + visited["linear_gemm"]
             tf = fl / t / 1e12
-            stages[STAGE_3B] = {"ms": t * 1e3, "bound": "tensor (3xTF32)", "achieved": tf, "unit": "TFLOP/s", "frac": tf / tf32_sus,
+            stages[STAGE_3B] = {"ms": t * 1e3, "bound": "tensor (3 fp16 MMAs per fp32 product)", "achieved": tf, "unit": "TFLOP/s", "frac": tf / f16_sus,
                                 "note": "visited-tile fp32 flops of the GEMMs / time of every stage-3b kernel incl. operand "
                                         "preparation; 3 MMAs per product cap this at 1/3"}
         for v in stages.values():

@@ -45,7 +45,8 @@ using namespace tc;
 constexpr int G_BM = 128;
 constexpr int G_BN = 256;      // == embed_dim
 constexpr int G_BK = 32;
-constexpr int G_THREADS = 320;
+constexpr int G_XF_WARPS = 8;                              // operand-transform warps
+constexpr int G_THREADS = 192 + 32 * G_XF_WARPS;
 constexpr int kABytes = G_BM * G_BK * 4;                 // 16 KB
 
 enum { EPI_STORE_ROWS = 0, EPI_LN_RELU_T = 1, EPI_LN_RELU_ROWS = 2, EPI_BIAS_ROWS = 3 };
@@ -81,7 +82,10 @@ struct GemmTcArgs {
     const unsigned *amax_a, *amax_b;
     unsigned *amax_out;
     int debug;      // timing experiments (SCHEMANET_GEMM_DEBUG): 1 transform skips its work, 2 no MMAs, 4 epilogue skips its work
+    long long *trace;   // SCHEMANET_GEMM_TRACE: per CTA 8 cycle counters (see launch_gemm3x_n), null in normal runs
 };
+#define TR_T0() const long long tr_t0_ = a.trace ? clock64() : 0
+#define TR_ADD(var) do { if (a.trace) var += clock64() - tr_t0_; } while (0)
 
 // power-of-two scale that puts a tensor whose largest magnitude has the bit pattern `bits` into [2^14, 2^15)
 __device__ __forceinline__ float scale_from_amax(unsigned bits)
@@ -155,11 +159,11 @@ __device__ __forceinline__ void split_pair(float x0, float x1, float s, uint32_t
     hi = *reinterpret_cast<const uint32_t *>(&hh);
     lo = *reinterpret_cast<const uint32_t *>(&ll);
 }
-// one 128-byte landing row (8 float4, already un-swizzled into k order) -> its 4 hi and 4 lo 16-byte chunks
-__device__ __forceinline__ void convert_row(const float4 (&v)[8], float s, uint32_t hi_base, uint32_t lo_base)
+// half of a 128-byte landing row (4 float4 in k order = 16 k-elements) -> its 2 hi and 2 lo 16-byte chunks
+__device__ __forceinline__ void convert_half_row(const float4 (&v)[4], float s, uint32_t hi_base, uint32_t lo_base)
 {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
         uint32_t h[4], l[4];
         split_pair(v[2 * c].x, v[2 * c].y, s, h[0], l[0]);
         split_pair(v[2 * c].z, v[2 * c].w, s, h[1], l[1]);
@@ -191,6 +195,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 {
     using P = GemmPlan<CTAS>;
     constexpr int S = P::kStages;
+    const long long tr_entry = a.trace ? clock64() : 0;
+    unsigned long long tr_gt0 = 0;
+    if (a.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_gt0));
     extern __shared__ uint8_t smem_raw[];
     // 1 KB alignment for the 128-byte-swizzled TMA tiles, as an OFFSET into the shared array: going through uintptr_t makes
     // the compiler lose the address space and emit 64-bit generic LD/ST for every shared-memory access of the epilogue
@@ -215,7 +222,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int i = threadIdx.x; i < a.N_total; i += G_THREADS) s_bias[i] = a.bias[i];
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
-        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4 * CTAS); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], G_XF_WARPS * CTAS); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * CTAS); }
         fence_barrier_init();
     }
@@ -256,6 +263,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (kblocks == 0) continue;
 #define TILE_LOOP_END }
 
+    long long tr0 = 0, tr1 = 0;                            // (trace: cycles this role spent waiting / working)
+    const long long tr_start = a.trace ? clock64() : 0;
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
@@ -263,7 +272,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             TILE_LOOP_BEGIN
                 for (int kidx = 0; kidx < kblocks; ++kidx) {
                     const int kb = kidx < kA ? kidx : k2s + (kidx - kA);
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    { TR_T0(); mbar_wait(&empty[stage], phase ^ 1); TR_ADD(tr0); }
                     uint8_t *s = smem + stage * P::kStage;
                     const int gb = a.batched_b ? g : 0;
                     // every CTA loads its own fp32 tiles (128 A rows, its share of the B tile) and tracks them on its OWN
@@ -274,6 +283,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             TILE_LOOP_END
+            if (a.trace) a.trace[blockIdx.x * 8 + 0] = tr0;
         }
     } else if (warp == 1) {
         if (rank == 0) {
@@ -281,11 +291,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             TILE_LOOP_BEGIN
-                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                { TR_T0(); mbar_wait(&tmem_empty[as], aphase ^ 1); TR_ADD(tr1); }
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * G_BN);
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&ready[stage], phase);             // fp16 hi/lo tiles of both CTAs' slots are in place
+                    { TR_T0(); mbar_wait(&ready[stage], phase); TR_ADD(tr0); }     // fp16 hi/lo tiles of both CTAs' slots are in place
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t s = smem_u32(smem + stage * P::kStage);
@@ -317,6 +327,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 }
                 if (++as == 2) { as = 0; aphase ^= 1; }
             TILE_LOOP_END
+            if (a.trace && lane == 0) { a.trace[blockIdx.x * 8 + 3] = tr0; a.trace[blockIdx.x * 8 + 4] = tr1; }
         }
     } else if (warp < 6) {
         const int wq = warp & 3;
@@ -324,7 +335,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         int as = 0;
         uint32_t aphase = 0;
         TILE_LOOP_BEGIN
-            mbar_wait(&tmem_full[as], aphase);
+            { TR_T0(); mbar_wait(&tmem_full[as], aphase); TR_ADD(tr0); }
+            const long long tr_w0 = a.trace ? clock64() : 0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * G_BN);
             const int m = mb * G_BM + row_in_tile;           // row inside this batch entry
@@ -458,45 +470,51 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tc_fence_before();
             __syncwarp();
             if (EPI == EPI_STORE_ROWS || EPI == EPI_LN_RELU_T) record_amax(a.amax_out, out_max);
+            if (a.trace) tr1 += clock64() - tr_w0;
             if (lane == 0) {
                 if (CTAS == 1) mbar_arrive(&tmem_empty[as]);
                 else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));   // the leader owns the accumulator ring
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         TILE_LOOP_END
+        if (a.trace && threadIdx.x == 64) { a.trace[blockIdx.x * 8 + 5] = tr0; a.trace[blockIdx.x * 8 + 6] = tr1; }
     } else {
         // ===================== operand transform: fp32 landing tiles -> fp16 hi / lo tiles, in place =====================
-        // Thread t owns landing row t of A and rows t (+128) of B: it reads the whole 128-byte rows (the 16-byte chunk c
-        // of row r was stored by TMA at position c ^ (r & 7); a quarter-warp touches 8 rows = 8 distinct chunk positions:
-        // no bank conflicts), waits until all 128 transform threads have read (the fp16 tiles overwrite other threads'
-        // landing rows), then writes its 4 + 4 chunks per row (a quarter-warp writes one contiguous 128-byte core matrix).
-        const int tid = (int)threadIdx.x - 6 * 32;                  // 0 .. 127
+        // Thread t owns HALF of landing row (t & 127) of A and of B (+128): k-elements 16 h .. 16 h + 15 with h = t >> 7.  It
+        // reads its four 16-byte pieces per row (piece c of row r was stored by TMA at position c ^ (r & 7); a quarter-warp
+        // touches 8 rows = 8 distinct positions: no bank conflicts), waits until all 256 transform threads have read (the fp16
+        // tiles overwrite other threads' landing rows), then writes its 2 + 2 chunks per row (a quarter-warp writes one
+        // contiguous 128-byte core matrix).  Eight warps: two per scheduler, so one's shared-memory latency hides under the
+        // other's conversions (four warps measured 1030 cycles per k-block against 768 for the MMAs).
+        const int tid = (int)threadIdx.x - 6 * 32;                  // 0 .. 255
+        const int trow = tid & 127, th = tid >> 7;
         const uint32_t ready_lead = mapa_u32(smem_u32(&ready[0]), 0);
-        const uint32_t swz = (uint32_t)(tid & 7);
-        const uint32_t row_off = (uint32_t)((tid >> 3) * 512 + (tid & 7) * 16);    // of row t inside an fp16 tile
+        const uint32_t swz = (uint32_t)(trow & 7);
+        const uint32_t row_off = (uint32_t)((trow >> 3) * 512 + (trow & 7) * 16 + th * 256);   // of this half row inside an fp16 tile
         constexpr int kBPer = P::kBRows / 128;                      // B rows per thread
         int stage = 0;
         uint32_t phase = 0;
         TILE_LOOP_BEGIN
             (void)nb; (void)mb;
             for (int kidx = 0; kidx < kblocks; ++kidx) {
-                mbar_wait(&full[stage], phase);                     // this CTA's fp32 tiles have landed
+                { TR_T0(); mbar_wait(&full[stage], phase); TR_ADD(tr0); }     // this CTA's fp32 tiles have landed
+                const long long tr_w0 = a.trace ? clock64() : 0;
                 const uint32_t sb = smem_u32(smem + stage * P::kStage);
-                float4 va[8], vb[kBPer][8];
+                float4 va[4], vb[kBPer][4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) va[c] = lds128(sb + (uint32_t)tid * 128u + (((uint32_t)c ^ swz) << 4));
+                for (int c = 0; c < 4; ++c) va[c] = lds128(sb + (uint32_t)trow * 128u + (((uint32_t)(4 * th + c) ^ swz) << 4));
 #pragma unroll
                 for (int h = 0; h < kBPer; ++h)
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        vb[h][c] = lds128(sb + kABytes + (uint32_t)(tid + 128 * h) * 128u + (((uint32_t)c ^ swz) << 4));
-                asm volatile("bar.sync 2, 128;" ::: "memory");       // every landing row is in registers
+                    for (int c = 0; c < 4; ++c)
+                        vb[h][c] = lds128(sb + kABytes + (uint32_t)(trow + 128 * h) * 128u + (((uint32_t)(4 * th + c) ^ swz) << 4));
+                asm volatile("bar.sync 2, %0;" ::"n"(32 * G_XF_WARPS) : "memory");       // every landing row is in registers
                 if (!(a.debug & 1)) {
-                    convert_row(va, scale_a, sb + row_off, sb + kABytes / 2 + row_off);
+                    convert_half_row(va, scale_a, sb + row_off, sb + kABytes / 2 + row_off);
 #pragma unroll
                     for (int h = 0; h < kBPer; ++h)
-                        convert_row(vb[h], scale_b, sb + kABytes + row_off + (uint32_t)(h * 16 * 512),
-                                    sb + kABytes + P::kBTile + row_off + (uint32_t)(h * 16 * 512));
+                        convert_half_row(vb[h], scale_b, sb + kABytes + row_off + (uint32_t)(h * 16 * 512),
+                                         sb + kABytes + P::kBTile + row_off + (uint32_t)(h * 16 * 512));
                 }
                 fence_proxy_async();                                // generic-proxy stores -> visible to the UMMA (async proxy)
                 __syncwarp();
@@ -504,9 +522,19 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     if (rank == 0) mbar_arrive(&ready[stage]);
                     else mbar_arrive_cluster(ready_lead + (uint32_t)(stage * 8));
                 }
+                if (a.trace) tr1 += clock64() - tr_w0;
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
         TILE_LOOP_END
+        if (a.trace && tid == 0) { a.trace[blockIdx.x * 8 + 1] = tr0; a.trace[blockIdx.x * 8 + 2] = tr1; }
+    }
+    if (a.trace && threadIdx.x == 0) a.trace[blockIdx.x * 8 + 7] = clock64() - tr_start;
+    if (a.trace && threadIdx.x == 32) {        // (second table after the first 8 * 512 entries)
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        a.trace[4096 + blockIdx.x * 4 + 0] = tr_start - tr_entry;
+        a.trace[4096 + blockIdx.x * 4 + 1] = (long long)tr_gt0;
+        a.trace[4096 + blockIdx.x * 4 + 2] = (long long)gt1;
     }
 #undef TILE_LOOP_BEGIN
 #undef TILE_LOOP_END
@@ -1194,6 +1222,14 @@ static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const c
     static const int dbg = [] { const char *e = getenv("SCHEMANET_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
     GemmTcArgs a2 = a;
     a2.debug = dbg;
+    // SCHEMANET_GEMM_TRACE=1: per-role wait / work cycle counters of every launch, printed after a device synchronisation
+    static const bool tracing = getenv("SCHEMANET_GEMM_TRACE") != nullptr;
+    static long long *trace_buf = nullptr;
+    if (tracing) {
+        if (!trace_buf) SH_CHECK_CUDA(cudaMalloc(&trace_buf, sizeof(long long) * 8 * 1024));
+        SH_CHECK_CUDA(cudaMemsetAsync(trace_buf, 0, sizeof(long long) * 8 * 1024, st));
+        a2.trace = trace_buf;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(num_units * CTAS);
     cfg.blockDim = dim3(G_THREADS);
@@ -1211,6 +1247,33 @@ static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const c
     prof_end(st);
     if (e != cudaSuccess) { set_error("%s launch -> %s", name, cudaGetErrorString(e)); return 1; }
     SH_CHECK_LAUNCH();
+    if (tracing) {
+        static long long host[8 * 1024];
+        SH_CHECK_CUDA(cudaStreamSynchronize(st));
+        SH_CHECK_CUDA(cudaMemcpy(host, trace_buf, sizeof(long long) * 8 * num_units * CTAS, cudaMemcpyDeviceToHost));
+        double m[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tmin = 1e30, tmax = 0;
+        for (int c = 0; c < num_units * CTAS; ++c) {
+            for (int j = 0; j < 8; ++j) m[j] += (double)host[c * 8 + j] / (num_units * CTAS);
+            tmin = host[c * 8 + 7] < tmin ? (double)host[c * 8 + 7] : tmin;
+            tmax = host[c * 8 + 7] > tmax ? (double)host[c * 8 + 7] : tmax;
+        }
+        {
+            static long long h2[4 * 512];
+            SH_CHECK_CUDA(cudaMemcpy(h2, trace_buf + 4096, sizeof(long long) * 4 * num_units * CTAS, cudaMemcpyDeviceToHost));
+            double pro = 0; long long g0 = (1LL << 62), g0max = 0, g1 = 0, g1min = (1LL << 62);
+            for (int c = 0; c < num_units * CTAS; ++c) {
+                pro += (double)h2[c * 4] / (num_units * CTAS);
+                g0 = h2[c * 4 + 1] < g0 ? h2[c * 4 + 1] : g0; g0max = h2[c * 4 + 1] > g0max ? h2[c * 4 + 1] : g0max;
+                g1 = h2[c * 4 + 2] > g1 ? h2[c * 4 + 2] : g1; g1min = h2[c * 4 + 2] < g1min ? h2[c * 4 + 2] : g1min;
+            }
+            fprintf(stderr, "gemm trace %-18s main loops min %.1f max %.1f kcyc | prologue %.1f kcyc | globaltimer: first entry -> last exit %.1f us, "
+                            "entry spread %.1f us, exit spread %.1f us\n", name, tmin / 1e3, tmax / 1e3, pro / 1e3, (g1 - g0) / 1e3,
+                    (g0max - g0) / 1e3, (g1 - g1min) / 1e3);
+        }
+        fprintf(stderr, "gemm trace %-18s units %4d ctas %3d | kcycles per CTA: total %.1f | producer wait-empty %.1f | transform wait-full %.1f "
+                        "work %.1f | mma(leader, x2) wait-ready %.1f wait-tmem %.1f | epilogue wait-full %.1f work %.1f\n",
+                name, units, num_units * CTAS, m[7] / 1e3, m[0] / 1e3, m[1] / 1e3, m[2] / 1e3, 2 * m[3] / 1e3, 2 * m[4] / 1e3, m[5] / 1e3, m[6] / 1e3);
+    }
     return 0;
 }
 

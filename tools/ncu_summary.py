@@ -3,6 +3,8 @@
 
   tools/ncu_summary.py launches gpurun_out/launches.csv            -> per-kernel launch list / share of the step
   tools/ncu_summary.py full gpurun_out/prof.ncu-rep                -> key metrics of every captured launch
+  tools/ncu_summary.py traffic gpurun_out/prof.ncu-rep             -> JSON {kernel: dram bytes / us per launch} (bench.py reads
+                                                                     the newest profiles/rNN_ncu_traffic.json for roofline.traffic)
 """
 import csv
 import subprocess
@@ -50,5 +52,30 @@ def full(path):
         print()
 
 
+def traffic(path):
+    """Per kernel (template name without arguments): the launch with the LARGEST dram traffic = the class-side launch of a
+    family, and the mean over its captured launches."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ik, it = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
+    rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}      # newer ncu builds name the units with or without 'second'
+    agg = {}
+    for r in rows[2:]:
+        name = r[ik].split("(")[0].replace("void ", "").replace("sh::", "").split("<")[0]
+        b = float(r[rd]) * scale.get(units[rd], 1.0) + float(r[wr]) * scale.get(units[wr], 1.0)
+        us = float(r[it]) * tscale.get(units[it].replace("second", "s").replace("usecond", "us"), 1.0)
+        agg.setdefault(name, []).append((b, us, r[ik][:80]))
+    res = {}
+    for name, v in agg.items():
+        top = max(v, key=lambda x: x[0])
+        res[name] = {"dram_bytes_per_launch": top[0], "us_per_launch_ncu": top[1], "launch": top[2],
+                     "launches_captured": len(v), "mean_dram_bytes": sum(x[0] for x in v) / len(v), "source": path.split("/")[-1]}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
