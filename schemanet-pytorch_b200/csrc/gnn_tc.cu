@@ -49,7 +49,13 @@ constexpr int G_XF_WARPS = 8;                              // operand-transform 
 constexpr int G_THREADS = 192 + 32 * G_XF_WARPS;
 constexpr int kABytes = G_BM * G_BK * 4;                 // 16 KB
 
-enum { EPI_STORE_ROWS = 0, EPI_LN_RELU_T = 1, EPI_LN_RELU_ROWS = 2, EPI_BIAS_ROWS = 3 };
+enum { EPI_STORE_ROWS = 0, EPI_LN_RELU_T = 1, EPI_LN_RELU_ROWS = 2, EPI_BIAS_ROWS = 3,
+       // embed_dim > 256: a LayerNorm row spans several 256-column accumulator tiles, which different work units own.  The
+       // epilogue stores z = acc + bias un-normalised (transposed for the next adjacency GEMM, or as rows for the pooling)
+       // together with the tile's (mean, M2) of every row; a tiny kernel merges the tiles' statistics (Chan's formula) and the
+       // CONSUMER normalises on the fly: the transform warps of the next adjacency GEMM while they convert the B operand, or
+       // the pooling kernel.  No separate LayerNorm pass over the activations, no round trip of H through HBM.
+       EPI_Z_T_STATS = 4, EPI_Z_ROWS_STATS = 5 };
 constexpr int kMaxDim = 1024;   // largest embed_dim the bias staging buffer holds
 
 struct GemmTcArgs {
@@ -81,6 +87,10 @@ struct GemmTcArgs {
     // slot this launch records the maximum of its own output in (null: the output is not a GEMM operand)
     const unsigned *amax_a, *amax_b;
     unsigned *amax_out;
+    float *stats;                // EPI_Z_*_STATS: [rows, N_total / 256, 2] per-tile (mean, M2) of z
+    // B operand = relu(LayerNorm(z)) of the stored z^T, applied by the transform warps (null: B is used as stored):
+    const float *bln_mr;         // [G * rows_per_graph, 2] merged (mean, rstd) per node
+    const float *bln_gamma, *bln_beta;   // [N_total]
     int debug;      // timing experiments (SCHEMANET_GEMM_DEBUG): 1 transform skips its work, 2 no MMAs, 4 epilogue skips its work
     long long *trace;   // SCHEMANET_GEMM_TRACE: per CTA 8 cycle counters (see launch_gemm3x_n), null in normal runs
 };
@@ -218,8 +228,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
     if (EPI == EPI_LN_RELU_T || EPI == EPI_LN_RELU_ROWS)
         for (int i = threadIdx.x; i < G_BN; i += G_THREADS) { s_bias[i] = a.bias[i]; s_gamma[i] = a.gamma[i]; s_beta[i] = a.beta[i]; }
-    if (EPI == EPI_BIAS_ROWS)
-        for (int i = threadIdx.x; i < a.N_total; i += G_THREADS) s_bias[i] = a.bias[i];
+    if (EPI == EPI_BIAS_ROWS || EPI == EPI_Z_T_STATS || EPI == EPI_Z_ROWS_STATS)
+        for (int i = threadIdx.x; i < a.N_total; i += G_THREADS) s_bias[i] = a.bias ? a.bias[i] : 0.0f;
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], G_XF_WARPS * CTAS); mbar_init(&empty[s], 1); }
@@ -368,6 +378,53 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], unscale, s_bias[nb * G_BN + c * 32 + j]);
                     store_chunk_rows(s_out + wq * 32 * 33, v, lane, o + c * 32, a.N_total, min(32, a.M_total - m_warp));
                 }
+            } else if (EPI == EPI_Z_T_STATS || EPI == EPI_Z_ROWS_STATS) {
+                // z = acc + bias of this 256-column tile (masked rows: z = 0, gnn.py:43-44) + the tile's LayerNorm statistics
+                const int gg = a.G > 1 ? g : m / a.rows_per_graph, i = a.G > 1 ? m : m % a.rows_per_graph;
+                const bool in_range = a.G > 1 ? m < a.rows_per_graph : m < a.M_total;
+                const int n_node = (in_range && a.row_sizes) ? a.row_sizes[gg] : a.rows_per_graph;
+                const bool valid = in_range && i < n_node;
+                const float *bias_t = s_bias + nb * G_BN;
+                float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f}, shift = 0.0f;
+#pragma unroll 1
+                for (int c = 0; c < G_BN / 32; ++c) {
+                    float v[32];
+                    tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = valid ? fmaf(v[j], unscale, bias_t[c * 32 + j]) : 0.0f;
+                    if (c == 0) {
+                        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) { q0 += v[j]; q1 += v[j + 1]; q2 += v[j + 2]; q3 += v[j + 3]; }
+                        shift = ((q0 + q1) + (q2 + q3)) * (1.0f / 32.0f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float tt = v[j] - shift;
+                        p1[j & 3] += tt;
+                        p2[j & 3] = fmaf(tt, tt, p2[j & 3]);
+                    }
+                    if (EPI == EPI_Z_T_STATS) {
+                        if (in_range) {
+                            float *o = a.out_t + ((size_t)gg * a.N_total + nb * G_BN + c * 32) * a.ldk + i;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) o[(size_t)j * a.ldk] = v[j];
+                        }
+                    } else {
+                        const int m_warp = mb * G_BM + wq * 32;
+                        const size_t row0 = (a.G > 1 ? (size_t)g * a.rows_per_graph : 0) + m_warp;
+                        store_chunk_rows(s_out + wq * 32 * 33, v, lane, a.out_rows + row0 * a.N_total + nb * G_BN + c * 32, a.N_total,
+                                         min(32, (a.G > 1 ? a.rows_per_graph : a.M_total) - m_warp));
+                    }
+                }
+                if (in_range) {
+                    const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
+                    const float dm = s1 / (float)G_BN;
+                    float2 st;
+                    st.x = shift + dm;                          // mean of the tile's 256 values
+                    st.y = fmaxf(s2 - s1 * dm, 0.0f);           // sum of squared deviations from it
+                    *reinterpret_cast<float2 *>(a.stats + (((size_t)gg * a.rows_per_graph + i) * nb_per + nb) * 2) = st;
+                }
             } else {
                 // z = acc + bias; LayerNorm over the 256 columns this thread owns; ReLU   (gnn.py:31,45)
                 // linear GEMM: flattened rows -> (graph, node); adjacency GEMM with a fused LayerNorm: (g, row in graph)
@@ -509,6 +566,27 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     for (int c = 0; c < 4; ++c)
                         vb[h][c] = lds128(sb + kABytes + (uint32_t)(trow + 128 * h) * 128u + (((uint32_t)(4 * th + c) ^ swz) << 4));
                 asm volatile("bar.sync 2, %0;" ::"n"(32 * G_XF_WARPS) : "memory");       // every landing row is in registers
+                if (a.bln_mr != nullptr) {
+                    // B holds z^T of the previous layer: h = relu((z - mean_k) rstd_k gamma_f + beta_f) for feature row f, node k
+                    const int kb = kidx < kA ? kidx : k2s + (kidx - kA);
+                    const int k0 = kb * G_BK + 16 * th;
+                    const float2 *mr = reinterpret_cast<const float2 *>(a.bln_mr) + (size_t)(a.batched_b ? g : 0) * a.rows_per_graph;
+#pragma unroll
+                    for (int h = 0; h < kBPer; ++h) {
+                        const int f = nb * G_BN + rank * P::kBRows + trow + 128 * h;
+                        const float gam = __ldg(a.bln_gamma + f), bet = __ldg(a.bln_beta + f);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            float *e = reinterpret_cast<float *>(&vb[h][c]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int k = k0 + 4 * c + j;
+                                const float2 s2 = k < a.rows_per_graph ? __ldg(mr + k) : make_float2(0.0f, 0.0f);
+                                e[j] = fmaxf(fmaf(e[j] - s2.x, s2.y * gam, bet), 0.0f);
+                            }
+                        }
+                    }
+                }
                 if (!(a.debug & 1)) {
                     convert_half_row(va, scale_a, sb + row_off, sb + kABytes / 2 + row_off);
 #pragma unroll
@@ -1080,17 +1158,81 @@ class_adj_raw_kernel(const float *__restrict__ ew, const float *__restrict__ row
     record_amax(amax, mx);
 }
 
-// largest magnitude of each layer's Linear weight matrix (the B operand of the linear GEMMs): one CTA per layer
-struct WeightPtrs { const float *w[16]; };
-__global__ void __launch_bounds__(256) weights_absmax_kernel(WeightPtrs p, int n, unsigned *amax)
+// amax slots: the adjacency, the Linear weights of layer l, the node features entering layer l (l = num_layers: never
+// consumed), the adjacency product Y of layer l
+constexpr int kMaxTcLayers = 16;
+constexpr int AM_ADJ = 0, AM_W = 1, AM_X = 1 + kMaxTcLayers, AM_Y = 2 + 2 * kMaxTcLayers;
+// a-priori bound of relu(LayerNorm_l(.)) = max_f |gamma_f| sqrt(D) + |beta_f| (operands normalised on the fly are never
+// materialised, so nothing can record their maximum), and the embedding table's maximum
+constexpr int AM_LN = 2 + 3 * kMaxTcLayers, AM_EMB = 2 + 4 * kMaxTcLayers;                    // 128 slots in all
+
+// Operand bounds that depend on the parameters only, one launch per forward.  blockIdx.y < layers: the largest magnitude of
+// layer y's Linear weights (B operand of the linear GEMMs) and, by block (0, y), the a-priori bound of that layer's
+// relu(LayerNorm(.)) output, max_f |gamma_f| sqrt(D) + |beta_f|  (|normalised value| <= sqrt(D - 1));
+// blockIdx.y == layers: the largest magnitude of the embedding table (A operand of the table product P_0 = Emb W_0^T).
+struct ParamPtrs { const float *w[16], *gamma[16], *beta[16]; const float *emb; long long emb_n; int layers; };
+__global__ void __launch_bounds__(256) param_bounds_kernel(ParamPtrs p, int D, unsigned *amax)
 {
-    const float4 *w = reinterpret_cast<const float4 *>(p.w[blockIdx.y]);
+    const int y = blockIdx.y;
     float mx = 0.0f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += gridDim.x * blockDim.x) {
-        const float4 v = __ldg(w + i);
-        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    if (y < p.layers) {
+        const float4 *w = reinterpret_cast<const float4 *>(p.w[y]);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D * D / 4; i += gridDim.x * blockDim.x) {
+            const float4 v = __ldg(w + i);
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+        record_amax(amax + AM_W + y, mx);
+        if (blockIdx.x == 0) {
+            float b = 0.0f;
+            const float rt = sqrtf((float)D);
+            for (int i = threadIdx.x; i < D; i += blockDim.x) b = fmaxf(b, fmaf(fabsf(p.gamma[y][i]), rt, fabsf(p.beta[y][i])));
+            record_amax(amax + AM_LN + y, b);
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.emb_n; i += (long long)gridDim.x * blockDim.x)
+            mx = fmaxf(mx, fabsf(__ldg(p.emb + i)));
+        record_amax(amax + AM_EMB, mx);
     }
-    record_amax(amax + blockIdx.y, mx);
+}
+
+// embed_dim > 256: merge the per-tile LayerNorm statistics of every row (Chan et al.: tiles of equal size T = 256) into
+// (mean, rstd):  mean = avg_t mean_t,  M2 = sum_t M2_t + T sum_t (mean_t - mean)^2,  rstd = 1 / sqrt(M2 / D + eps)
+__global__ void __launch_bounds__(256)
+ln_stats_merge_kernel(const float *__restrict__ stats, int64_t rows, int nt, float eps, float *__restrict__ mr)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float2 *s = reinterpret_cast<const float2 *>(stats) + r * nt;
+    float mean = 0.0f;
+    for (int t = 0; t < nt; ++t) mean += s[t].x;
+    mean /= (float)nt;
+    float m2 = 0.0f;
+    for (int t = 0; t < nt; ++t) { const float dlt = s[t].x - mean; m2 += s[t].y + (float)G_BN * dlt * dlt; }
+    reinterpret_cast<float2 *>(mr)[r] = make_float2(mean, 1.0f / sqrtf(m2 / (float)(nt * G_BN) + eps));
+}
+
+// embed_dim > 256, last layer: pooled partials straight from the un-normalised z rows,
+//   partial[g, chunk, d] = sum over the chunk's nodes of relu((z[g,i,d] - mean_i) rstd_i gamma_d + beta_d) * w[g, i]   (gnn.py:45,94-95)
+__global__ void __launch_bounds__(256)
+pool_ln_rows_kernel(const float *__restrict__ Z, const float *__restrict__ mr, const float *__restrict__ gamma,
+                    const float *__restrict__ beta, const float *__restrict__ vertex_w, int ld_v, const int32_t *__restrict__ sizes,
+                    int n_fixed, int D, int chunks, float *__restrict__ partial)
+{
+    const int g = blockIdx.y, chunk = blockIdx.x;
+    const int n_g = sizes ? sizes[g] : n_fixed;
+    const int per = ceil_div(n_fixed, chunks);
+    const int r0 = chunk * per, r1 = min(n_g, r0 + per);
+    const float2 *mrg = reinterpret_cast<const float2 *>(mr) + (size_t)g * n_fixed;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float gam = gamma[d], bet = beta[d];
+        float acc = 0.0f;
+        for (int r = r0; r < r1; ++r) {
+            const float2 s = mrg[r];
+            const float h = fmaxf(fmaf(Z[((size_t)g * n_fixed + r) * D + d] - s.x, s.y * gam, bet), 0.0f);
+            acc = fmaf(h, vertex_w[(size_t)g * ld_v + r], acc);
+        }
+        partial[((size_t)g * chunks + chunk) * D + d] = acc;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1153,6 +1295,7 @@ bool gnn_tc_supported(int D, int n_fixed)
 struct TcBuffers {
     float *adj, *xt, *xt2, *y, *tab, *h_rows;     // tab: (M+1)-row table scratch (P_0 = Emb W_0^T), same size as y
     unsigned *amax;                               // operand maxima (bit patterns), see AM_* below; zeroed per forward
+    float *stats, *mr;                            // embed_dim > 256: per-tile LayerNorm statistics and the merged (mean, rstd)
     int32_t *n_act, *old_of_new;
     float *rowinv, *pool_extra, *pool_groups;
     int64_t *pid;
@@ -1182,7 +1325,9 @@ static TcBuffers carve_tc(void *base, int G, int n_fixed, int D)
     b.pool_groups = (float *)(p + off); off += al256(((size_t)G * n_fixed / 32 + 2) * 2 * D * 4);
     b.pid = (int64_t *)(p + off); off += al256((size_t)G * n_fixed * 8);
     b.pvw = (float *)(p + off); off += al256((size_t)G * n_fixed * 4);
-    b.amax = (unsigned *)(p + off); off += 256;
+    b.amax = (unsigned *)(p + off); off += 512;
+    b.stats = (float *)(p + off); off += al256((size_t)G * n_fixed * (D / G_BN) * 2 * 4);
+    b.mr = (float *)(p + off); off += al256((size_t)G * n_fixed * 2 * 4);
     b.bytes = off;
     return b;
 }
@@ -1192,11 +1337,6 @@ size_t gnn_tc_workspace_bytes(int G, int n_fixed, int D, int chunks)
     (void)chunks;
     return carve_tc(nullptr, G, n_fixed, D).bytes + 4096;
 }
-
-// amax slots: the adjacency, the Linear weights of layer l, the node features entering layer l (l = num_layers: never
-// consumed), the adjacency product Y of layer l
-constexpr int kMaxTcLayers = 16;
-constexpr int AM_ADJ = 0, AM_W = 1, AM_X = 1 + kMaxTcLayers, AM_Y = 2 + 2 * kMaxTcLayers;     // 64 slots in all
 
 static int gemm_ctas()
 {
@@ -1308,6 +1448,15 @@ static bool layer0_fused(const sh_gnn_params *p, int G, int n_fixed)
 {
     return p->embed_dim == G_BN && (int64_t)(p->num_codes + 1) <= (int64_t)G * n_fixed;
 }
+// embed_dim > 256 (ImageNet configuration: 1024): the same layer-0 shortcut -- the first Linear is applied to the (M+1)-row
+// embedding table, on the tensor cores -- and LayerNorm applied by the consumers of z (EPI_Z_*_STATS), see run_layers_wide
+static bool wide_fused(const sh_gnn_params *p, int G, int n_fixed)
+{
+    static const bool off = getenv("SCHEMANET_WIDE_UNFUSED") != nullptr;
+    return !off && p->embed_dim > G_BN && (int64_t)(p->num_codes + 1) <= (int64_t)G * n_fixed;
+}
+static int tmap3(CUtensorMap *m, const float *p, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld, uint64_t bstride,
+                 uint32_t box_rows);
 
 // The (M+1)-row table work of a forward (layer-0 product P_0, the activation tables of the class side, the pooled share of
 // its pruned vertices) depends on the parameters only -- not on the adjacency operand -- and consists of small,
@@ -1343,12 +1492,33 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
     SH_REQUIRE(p->num_layers <= kMaxTcLayers, "gnn: at most %d layers on the tensor-core path", kMaxTcLayers);
     // operand maxima of this forward: reset, then the Linear weights' (every other slot is written by the kernel that
     // produces the operand)
-    SH_CHECK_CUDA(cudaMemsetAsync(b.amax, 0, 256, st));
+    SH_CHECK_CUDA(cudaMemsetAsync(b.amax, 0, 512, st));
     {
-        WeightPtrs wp{};
-        for (int l = 0; l < p->num_layers; ++l) wp.w[l] = p->lin_w[l];
-        SH_LAUNCH("gnn_weights_absmax", st, weights_absmax_kernel<<<dim3(16, p->num_layers), 256, 0, st>>>(wp, D * D, b.amax + AM_W));
+        ParamPtrs pp{};
+        for (int l = 0; l < p->num_layers; ++l) { pp.w[l] = p->lin_w[l]; pp.gamma[l] = p->ln_w[l]; pp.beta[l] = p->ln_b[l]; }
+        pp.emb = p->embedding; pp.emb_n = (long long)(p->num_codes + 1) * D; pp.layers = p->num_layers;
+        const bool wide_tables = D > G_BN && wide_fused(p, G, n_fixed);       // (only that path multiplies the embedding table on the tensor cores)
+        SH_LAUNCH("gnn_param_bounds", st, param_bounds_kernel<<<dim3(16, p->num_layers + (wide_tables ? 1 : 0)), 256, 0, st>>>(pp, D, b.amax));
         SH_CHECK_LAUNCH();
+    }
+    if (wide_fused(p, G, n_fixed)) {
+        // P_0 = Emb W_0^T into tab on the tensor cores (no bias here: b_0 is added after the adjacency product), then X_0^T = the
+        // rows of P_0 gathered by node id
+        SH_REQUIRE((((uintptr_t)p->embedding | (uintptr_t)p->lin_w[0]) & 15) == 0, "gnn: parameters must be 16-byte aligned for TMA");
+        const int rows = p->num_codes + 1;
+        CUtensorMap em, wm, wm2;
+        if (tmap3(&em, p->embedding, D, rows, 1, D, 0, G_BM)) return 1;
+        if (tmap3(&wm, p->lin_w[0], D, D, 1, D, 0, G_BN)) return 1;
+        if (tmap3(&wm2, p->lin_w[0], D, D, 1, D, 0, G_BN / 2)) return 1;
+        GemmTcArgs c{};
+        c.G = 1; c.rows_per_graph = rows; c.M_total = rows; c.K_total = D; c.N_total = D; c.batched_b = 0;
+        c.out_rows = b.tab; c.amax_a = b.amax + AM_EMB; c.amax_b = b.amax + AM_W;
+        CUtensorMap m[2] = {em, wm}, mp[2] = {em, wm2};
+        if (launch_gemm3x<EPI_BIAS_ROWS>(m, mp, c, "gnn_embed_table_tc", st)) return 1;
+        dim3 grid2(ceil_div(b.ldk, 32), ceil_div(D, 256), G);
+        SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(b.tab, ids, ld_ids, row_sizes, n_fixed, b.ldk, D, b.xt, b.amax + AM_X));
+        SH_CHECK_LAUNCH();
+        return 0;
     }
     if (!layer0_fused(p, G, n_fixed)) return 0;
     static const bool serial = getenv("SCHEMANET_TABLES_INLINE") != nullptr;
@@ -1395,6 +1565,71 @@ static int tables_join(const sh_gnn_params *p, int G, int n_fixed, cudaStream_t 
     return 0;
 }
 
+// embed_dim > 256 with the layer-0 shortcut (wide_fused).  Per layer l (z_l = the pre-LayerNorm activations):
+//   l = 0:  z_0 = Adj (P_0 rows) + b_0                                  one adjacency GEMM, epilogue stores z_0 (+ tile statistics)
+//   l > 0:  Y = Adj relu(LN_{l-1}(z_{l-1}))                             adjacency GEMM, LayerNorm + ReLU applied to the B operand by the
+//           z_l = Y W_l^T + b_l                                         transform warps; linear GEMM, epilogue stores z_l (+ statistics)
+//   end:    pooled = sum_i relu(LN_{L-1}(z_{L-1}))_i w_i                 pool_ln_rows_kernel, straight from the z rows
+// z is stored transposed (the next adjacency GEMM's K-major B operand) except for the last layer (rows, for the pooling).
+static int run_layers_wide(const sh_gnn_params *p, int G, int n_fixed, const int32_t *k_sizes, int identity_tail,
+                           const int32_t *row_sizes, const float *vertex_w, int ld_v, const TcBuffers &b, int chunks, float *partial,
+                           cudaStream_t st)
+{
+    const int D = p->embed_dim, ldk = b.ldk, nt = D / G_BN, L = p->num_layers;
+    const int64_t rows = (int64_t)G * n_fixed;
+    CUtensorMap adjm, ym;
+    if (tmap3(&adjm, b.adj, n_fixed, n_fixed, G, ldk, (uint64_t)n_fixed * ldk, G_BM)) return 1;
+    if (tmap3(&ym, b.y, D, (uint64_t)rows, 1, D, 0, G_BM)) return 1;
+    float *xin = b.xt, *xout = b.xt2;
+    auto merge = [&]() -> int {
+        SH_LAUNCH("gnn_ln_stats_merge", st, ln_stats_merge_kernel<<<(unsigned)ceil_div64(rows, 256), 256, 0, st>>>(b.stats, rows, nt, p->ln_eps, b.mr));
+        SH_CHECK_LAUNCH();
+        return 0;
+    };
+    for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        CUtensorMap xtm, xtm2;
+        if (tmap3(&xtm, xin, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN)) return 1;
+        if (tmap3(&xtm2, xin, n_fixed, D, G, ldk, (uint64_t)D * ldk, G_BN / 2)) return 1;
+        CUtensorMap m1[2] = {adjm, xtm}, m1p[2] = {adjm, xtm2};
+        GemmTcArgs a{};
+        a.G = G; a.rows_per_graph = n_fixed; a.M_total = n_fixed; a.K_total = n_fixed; a.N_total = D;
+        a.k_sizes = k_sizes; a.identity_tail = identity_tail; a.batched_b = 1;
+        a.amax_a = b.amax + AM_ADJ; a.ldk = ldk; a.stats = b.stats; a.eps = p->ln_eps;
+        if (l == 0) {
+            a.amax_b = b.amax + AM_X; a.row_sizes = row_sizes; a.bias = p->lin_b[0];
+            if (last) { a.out_rows = b.h_rows; if (launch_gemm3x<EPI_Z_ROWS_STATS>(m1, m1p, a, "gnn_adj_z_tc", st)) return 1; }
+            else { a.out_t = xout; if (launch_gemm3x<EPI_Z_T_STATS>(m1, m1p, a, "gnn_adj_z_tc", st)) return 1; }
+            if (merge()) return 1;
+            float *t = xin; xin = xout; xout = t;
+            continue;
+        }
+        // Y = Adj relu(LN(z_{l-1})): the B operand is normalised while it is converted
+        a.bln_mr = b.mr; a.bln_gamma = p->ln_w[l - 1]; a.bln_beta = p->ln_b[l - 1];
+        a.amax_b = b.amax + AM_LN + (l - 1);
+        a.out_rows = b.y; a.amax_out = b.amax + AM_Y + l;
+        if (launch_gemm3x<EPI_STORE_ROWS>(m1, m1p, a, "gnn_adj_gemm_tc", st)) return 1;
+        // z_l = Y W_l^T + b_l
+        SH_REQUIRE(((uintptr_t)p->lin_w[l] & 15) == 0, "gnn: Linear weights must be 16-byte aligned for TMA");
+        CUtensorMap wm, wm2;
+        if (tmap3(&wm, p->lin_w[l], D, D, 1, D, 0, G_BN)) return 1;
+        if (tmap3(&wm2, p->lin_w[l], D, D, 1, D, 0, G_BN / 2)) return 1;
+        GemmTcArgs c{};
+        c.G = 1; c.rows_per_graph = n_fixed; c.M_total = (int)rows; c.K_total = D; c.N_total = D; c.row_sizes = row_sizes; c.batched_b = 0;
+        c.bias = p->lin_b[l]; c.eps = p->ln_eps; c.ldk = ldk; c.stats = b.stats;
+        c.amax_a = b.amax + AM_Y + l; c.amax_b = b.amax + AM_W + l;
+        CUtensorMap m2[2] = {ym, wm}, m2p[2] = {ym, wm2};
+        if (last) { c.out_rows = b.h_rows; if (launch_gemm3x<EPI_Z_ROWS_STATS>(m2, m2p, c, "gnn_linear_z_tc", st)) return 1; }
+        else { c.out_t = xin; if (launch_gemm3x<EPI_Z_T_STATS>(m2, m2p, c, "gnn_linear_z_tc", st)) return 1; }
+        if (merge()) return 1;
+    }
+    dim3 grid(chunks, G);
+    SH_LAUNCH("gnn_pool_ln_rows", st, pool_ln_rows_kernel<<<grid, 256, 0, st>>>(b.h_rows, b.mr, p->ln_w[L - 1], p->ln_b[L - 1], vertex_w, ld_v,
+                                                                                row_sizes, n_fixed, D, chunks, partial));
+    SH_CHECK_LAUNCH();
+    return 0;
+}
+
 // tables_begin() must have been called on `st` before (after the kernels that produce ids / vertex_w / row_sizes).
 static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32_t *k_sizes, int identity_tail,
                          const int32_t *row_sizes, const int64_t *ids, int ld_ids, const float *vertex_w, int ld_v,
@@ -1406,6 +1641,8 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     // the (M+1)-row embedding TABLE once (a tiny fp32 GEMM) instead of to every node of every graph; layer 0 then is a
     // single adjacency GEMM with bias + LayerNorm + ReLU fused in its epilogue.  The table product is staged in the
     // `tab` buffer (as large as Y), which it fits whenever the batch has at least M+1 node slots.
+    if (wide_fused(p, G, n_fixed))
+        return run_layers_wide(p, G, n_fixed, k_sizes, identity_tail, row_sizes, vertex_w, ld_v, b, chunks, partial, st);
     const bool fuse0 = layer0_fused(p, G, n_fixed);
     SH_REQUIRE(!table_tail || (fuse0 && row_sizes && !identity_tail), "run_layers_tc: table tail needs the fused layer 0");
     const float *table = fuse0 ? b.tab : p->embedding;
@@ -1547,7 +1784,7 @@ int gnn_class_forward_tc(const sh_gnn_params *p, int K, int Vc, const float *cla
               class_perm_kernel<<<K, 1024, 0, st>>>(class_vertices, class_ingredients, Vc, prune_threshold, prune, b.n_act,
                                                     b.old_of_new, b.pid, b.pvw));
     SH_CHECK_LAUNCH();
-    if (tables_begin(p, K, Vc, b.n_act, b.pid, Vc, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;
+    if (tables_begin(p, K, Vc, class_table_tail(p, K, Vc) ? b.n_act : nullptr, b.pid, Vc, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;   // (identity tail: every vertex keeps its GEMM row)
     SH_LAUNCH("class_adj_prep_kernel", st,
               class_adj_prep_kernel<<<dim3(ceil_div(b.ldk, 32), ceil_div(Vc, 32), K), 256, 0, st>>>(
                   class_edges, K, Vc, b.ldk, G_BM * gemm_ctas(), class_table_tail(p, K, Vc) ? 0 : 1, b.n_act, b.old_of_new,
@@ -1571,7 +1808,7 @@ int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc
               class_perm_kernel<<<K, 1024, 0, st>>>(class_vertices, class_ingredients, Vc, prune_threshold, prune, b.n_act,
                                                     b.old_of_new, b.pid, b.pvw));
     SH_CHECK_LAUNCH();
-    if (tables_begin(p, K, Vc, b.n_act, b.pid, Vc, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;
+    if (tables_begin(p, K, Vc, class_table_tail(p, K, Vc) ? b.n_act : nullptr, b.pid, Vc, b.pvw, b, st, class_table_tail(p, K, Vc))) return 1;   // (identity tail: every vertex keeps its GEMM row)
     // (Measured and not kept, r02: ONE kernel with a cluster of 4 / 8 CTAs per class -- normalisers in phase 1, cluster barrier,
     // adjacency gathered from L2 in phase 2.  189-203 us against 90 + 77 us for the two kernels below: a class only gets its
     // cluster's share of the HBM bandwidth, HBM idles during phase 2, and 18-37 classes in flight leave the latency-bound gather

@@ -562,6 +562,37 @@ def test_gnn_tensor_core_path_vs_oracle(K, Vc, masked, D):
     rel_close(got, want, what="gnn tensor-core path")
 
 
+@pytest.mark.parametrize("G,n,masked,D,M,layers", [(6, 100, True, 512, 300, 2), (4, 300, False, 1024, 700, 2), (5, 196, True, 1024, 500, 2),
+                                                   (3, 160, True, 512, 200, 3), (4, 96, True, 768, 100, 1)])
+def test_gnn_wide_fused_path_vs_oracle(G, n, masked, D, M, layers):
+    """embed_dim > 256 with at least M + 1 node slots: the first Linear is applied to the embedding table on the tensor
+    cores, every GEMM epilogue stores the pre-LayerNorm activations with per-tile statistics, and LayerNorm + ReLU are
+    applied by the consumer (the next adjacency GEMM's operand conversion, the pooling).  1, 2 and 3 layers."""
+    from schema_inference.graph import Matcher
+    gen = torch.Generator().manual_seed(90 + n + D)
+    params = ho.synth_gnn(M, D, seed=91, num_layers=layers)
+    for i in range(layers):
+        params[f"layers.{i}.norm.weight"] = torch.rand(D, generator=gen) + 0.5
+        params[f"layers.{i}.norm.bias"] = torch.randn(D, generator=gen) * 0.2
+    m = Matcher("inner_product", M, dict(embed_dim=D, num_layers=layers)).cuda()
+    m.gnn.load_state_dict(params)
+    nodes = torch.rand(G, n, generator=gen) / n
+    edges = torch.rand(G, n, n, generator=gen) / n
+    ids = torch.randint(0, M, (G, n), generator=gen)
+    mask = None
+    if masked:
+        sizes = torch.randint(1, n + 1, (G,), generator=gen)
+        sizes[0] = n
+        mask = torch.arange(n)[None, :] >= sizes[:, None]
+        nodes[mask] = 0
+        ids[mask] = M
+        edges = edges * (~mask)[:, :, None] * (~mask)[:, None, :]
+    want = ho.gnn_forward(params, nodes, edges, ids, mask, num_layers=layers)
+    with torch.no_grad():
+        got = m.gnn(nodes.cuda(), edges.cuda(), ids.cuda(), mask.cuda() if masked else None)
+    rel_close(got, want, what="gnn wide fused path")
+
+
 class _FakeBackbone(torch.nn.Module):
     """Stands in for the reference's JIT backbone: returns fixed `mid_feat` / `extracted` taps."""
 
@@ -659,11 +690,13 @@ def test_full_head_vs_oracle_cfg2():
     rel_close(gh.replay()["pred"], ref["pred"], what="cfg2 logits (graph replay)")
 
 
-@pytest.mark.parametrize("side,G,n,D", [("class", 48, 1024, 256), ("instance", 160, 196, 256), ("class", 24, 500, 1024)])
-def test_gnn_more_tiles_than_cta_pairs(side, G, n, D):
+@pytest.mark.parametrize("side,G,n,D,thr", [("class", 48, 1024, 256, 0.001), ("instance", 160, 196, 256, None),
+                                            ("class", 24, 500, 1024, 0.001), ("class", 8, 304, 512, 0.0034)])
+def test_gnn_more_tiles_than_cta_pairs(side, G, n, D, thr):
     """gemm3x_kernel is persistent: with more work units than CTA pairs (74 on a B200) every CTA walks several tiles.
     class: 48 x 4 = 192 units of 256 rows (fused class side incl. the pruned-vertex tables); instance: 160 graphs;
-    wide: D=1024 has 4 column tiles per row block."""
+    wide: D=1024 has 4 column tiles per row block (layer-0 shortcut on the tensor cores, LayerNorm applied by the consumers;
+    pruned vertices keep their GEMM rows through the identity tail -- the last case prunes more than half of them)."""
     from schemanet_b200 import native
     from schema_inference.graph import GNN, Matcher
     M = 1200
@@ -673,8 +706,8 @@ def test_gnn_more_tiles_than_cta_pairs(side, G, n, D):
         gnn = GNN(M, D, num_layers=2).cuda()
         gnn.load_state_dict(params)
         _, _, f = native.class_side(gnn.param_pack(), sch["vertex_weights"].cuda(), sch["edge_weights"].clone().cuda(),
-                                    sch["class_ingredients"].cuda(), 0.001, True, False, want_edges=False)
-        atlas = ho.class_atlas(sch["vertex_weights"], sch["edge_weights"].clone(), sch["class_ingredients"], 0.001, False)
+                                    sch["class_ingredients"].cuda(), thr, True, False, want_edges=False)
+        atlas = ho.class_atlas(sch["vertex_weights"], sch["edge_weights"].clone(), sch["class_ingredients"], thr, False)
         want = ho.gnn_forward(params, atlas["class_vertices"], atlas["class_edges"], sch["class_ingredients"], None)
         rel_close(f, want, what="class side, multi-tile")
     else:
