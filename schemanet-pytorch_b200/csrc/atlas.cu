@@ -47,7 +47,7 @@ class_edges_fast_kernel(float *__restrict__ ew, const float *__restrict__ cv, in
                         int prune_in_place, int remove_self_loop, float *__restrict__ ce, float *__restrict__ rowinv)
 {
     constexpr int RUN = 8;
-    const int units_per_class = Vc / RUN;
+    const int units_per_class = (Vc + RUN - 1) / RUN;
     const int64_t units = (int64_t)K * units_per_class;
     const int wpb = blockDim.x >> 5;
     for (int64_t u = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); u < units; u += (int64_t)gridDim.x * wpb)
@@ -112,10 +112,11 @@ int launch_class_edges(float *edge_weights, const float *class_vertices, int K, 
 {
     const int prune = prune_threshold >= 0.0f ? 1 : 0;
     const int64_t rows = (int64_t)K * Vc;
-    const bool aligned = (Vc % 8 == 0) && ((reinterpret_cast<uintptr_t>(edge_weights) | reinterpret_cast<uintptr_t>(class_edges) |
+    // float4 accesses: every row must start on a 16-byte boundary (Vc % 4 == 0; ImageNet's Vc = 500 qualifies)
+    const bool aligned = (Vc % 4 == 0) && ((reinterpret_cast<uintptr_t>(edge_weights) | reinterpret_cast<uintptr_t>(class_edges) |
                                            reinterpret_cast<uintptr_t>(class_vertices)) % 16 == 0);
     if (aligned && Vc <= 1024) {
-        const int grid = (int)min(ceil_div64(rows / 8, 8), (int64_t)sm_count() * 16);
+        const int grid = (int)min(ceil_div64((int64_t)K * ((Vc + 7) / 8), 8), (int64_t)sm_count() * 16);
         if (Vc <= 512)
             SH_LAUNCH("class_edges_kernel", st, class_edges_fast_kernel<4><<<grid, 256, 0, st>>>(edge_weights, class_vertices, K, Vc, prune_threshold, prune,
                                                         prune_in_place, remove_self_loop, class_edges, rowinv));

@@ -41,12 +41,13 @@ __device__ __forceinline__ void class_edges_run(float *__restrict__ ew, const fl
         const int j = (c * kWarp + lane) * 4;
         nxt[c] = (j < Vc) ? *reinterpret_cast<const float4 *>(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    const int run = min(RUN, Vc - i0);          // (the last run of a class is short when Vc % 8 != 0)
 #pragma unroll 1
-    for (int r = 0; r < RUN; ++r) {
+    for (int r = 0; r < run; ++r) {
         const int i = i0 + r;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) cur[c] = nxt[c];
-        if (r + 1 < RUN) {
+        if (r + 1 < run) {
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 const int j = (c * kWarp + lane) * 4;

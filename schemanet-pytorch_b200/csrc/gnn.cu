@@ -521,6 +521,15 @@ extern "C" int sh_dev_similarity(const float *feat_instance, const float *feat_c
                                  float *logits, sh_stream_t stream)
 {
     SH_REQUIRE(B > 0 && K > 0 && D > 0 && kind >= 0 && kind <= 2, "similarity: bad arguments");
+    if (kind == SH_SIM_INNER_PRODUCT && K <= 1024 && similarity_tc_supported(B, K, D) && getenv("SCHEMANET_GNN_SIMT") == nullptr) {
+        // ImageNet scale (1024 x 1000 x 1024): the logits are a real GEMM -> tensor cores (one warp per pair costs 0.48 ms)
+        static unsigned *scratch[64] = {nullptr};
+        int dev = 0;
+        SH_CHECK_CUDA(cudaGetDevice(&dev));
+        SH_REQUIRE(dev >= 0 && dev < 64, "similarity: device index out of range");
+        if (!scratch[dev]) SH_CHECK_CUDA(cudaMalloc(&scratch[dev], 256));
+        return similarity_tc(feat_instance, feat_class, B, K, D, logits, scratch[dev], (cudaStream_t)stream);
+    }
     const int64_t pairs = (int64_t)B * K;
     const int grid = (int)min(ceil_div64(pairs, 8), (int64_t)sm_count() * 16);
     SH_LAUNCH("similarity_kernel", (cudaStream_t)stream, similarity_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat_instance, feat_class, B, K, D, kind, logits));

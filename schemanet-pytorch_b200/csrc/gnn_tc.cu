@@ -87,6 +87,7 @@ struct GemmTcArgs {
     // slot this launch records the maximum of its own output in (null: the output is not a GEMM operand)
     const unsigned *amax_a, *amax_b;
     unsigned *amax_out;
+    int n_valid;                 // EPI_BIAS_ROWS: output columns that exist (0: all N_total); the row stride is n_valid then
     float *stats;                // EPI_Z_*_STATS: [rows, N_total / 256, 2] per-tile (mean, M2) of z
     // B operand = relu(LayerNorm(z)) of the stored z^T, applied by the transform warps (null: B is used as stored):
     const float *bln_mr;         // [G * rows_per_graph, 2] merged (mean, rstd) per node
@@ -376,7 +377,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], unscale, s_bias[nb * G_BN + c * 32 + j]);
-                    store_chunk_rows(s_out + wq * 32 * 33, v, lane, o + c * 32, a.N_total, min(32, a.M_total - m_warp));
+                    if (a.n_valid == 0) {
+                        store_chunk_rows(s_out + wq * 32 * 33, v, lane, o + c * 32, a.N_total, min(32, a.M_total - m_warp));
+                    } else if (m < a.M_total) {
+                        // ragged output width (logits [B, K]): this thread's row, the columns that exist
+                        float *orow = a.out_rows + (size_t)m * a.n_valid + nb * G_BN + c * 32;
+                        const int cols = a.n_valid - (nb * G_BN + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < cols) orow[j] = v[j];
+                    }
                 }
             } else if (EPI == EPI_Z_T_STATS || EPI == EPI_Z_ROWS_STATS) {
                 // z = acc + bias of this 256-column tile (masked rows: z = 0, gnn.py:43-44) + the tile's LayerNorm statistics
@@ -1164,13 +1174,13 @@ constexpr int kMaxTcLayers = 16;
 constexpr int AM_ADJ = 0, AM_W = 1, AM_X = 1 + kMaxTcLayers, AM_Y = 2 + 2 * kMaxTcLayers;
 // a-priori bound of relu(LayerNorm_l(.)) = max_f |gamma_f| sqrt(D) + |beta_f| (operands normalised on the fly are never
 // materialised, so nothing can record their maximum), and the embedding table's maximum
-constexpr int AM_LN = 2 + 3 * kMaxTcLayers, AM_EMB = 2 + 4 * kMaxTcLayers;                    // 128 slots in all
+constexpr int AM_LN = 2 + 3 * kMaxTcLayers, AM_EMB = 2 + 4 * kMaxTcLayers, AM_FC = AM_EMB + 1, AM_POOL = AM_EMB + 2;   // 128 slots in all
 
 // Operand bounds that depend on the parameters only, one launch per forward.  blockIdx.y < layers: the largest magnitude of
 // layer y's Linear weights (B operand of the linear GEMMs) and, by block (0, y), the a-priori bound of that layer's
 // relu(LayerNorm(.)) output, max_f |gamma_f| sqrt(D) + |beta_f|  (|normalised value| <= sqrt(D - 1));
 // blockIdx.y == layers: the largest magnitude of the embedding table (A operand of the table product P_0 = Emb W_0^T).
-struct ParamPtrs { const float *w[16], *gamma[16], *beta[16]; const float *emb; long long emb_n; int layers; };
+struct ParamPtrs { const float *w[16], *gamma[16], *beta[16]; const float *emb, *fc; long long emb_n; int layers; };
 __global__ void __launch_bounds__(256) param_bounds_kernel(ParamPtrs p, int D, unsigned *amax)
 {
     const int y = blockIdx.y;
@@ -1188,6 +1198,9 @@ __global__ void __launch_bounds__(256) param_bounds_kernel(ParamPtrs p, int D, u
             for (int i = threadIdx.x; i < D; i += blockDim.x) b = fmaxf(b, fmaf(fabsf(p.gamma[y][i]), rt, fabsf(p.beta[y][i])));
             record_amax(amax + AM_LN + y, b);
         }
+    } else if (y == p.layers) {                 // fc weights (the pooled features are multiplied by them on the tensor cores)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D * D; i += gridDim.x * blockDim.x) mx = fmaxf(mx, fabsf(__ldg(p.fc + i)));
+        record_amax(amax + AM_FC, mx);
     } else {
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.emb_n; i += (long long)gridDim.x * blockDim.x)
             mx = fmaxf(mx, fabsf(__ldg(p.emb + i)));
@@ -1233,6 +1246,14 @@ pool_ln_rows_kernel(const float *__restrict__ Z, const float *__restrict__ mr, c
         }
         partial[((size_t)g * chunks + chunk) * D + d] = acc;
     }
+}
+
+// max |x| of a small tensor into an amax slot
+__global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x, int64_t n, unsigned *slot)
+{
+    float mx = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mx = fmaxf(mx, fabsf(__ldg(x + i)));
+    record_amax(slot, mx);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1496,9 +1517,9 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
     {
         ParamPtrs pp{};
         for (int l = 0; l < p->num_layers; ++l) { pp.w[l] = p->lin_w[l]; pp.gamma[l] = p->ln_w[l]; pp.beta[l] = p->ln_b[l]; }
-        pp.emb = p->embedding; pp.emb_n = (long long)(p->num_codes + 1) * D; pp.layers = p->num_layers;
-        const bool wide_tables = D > G_BN && wide_fused(p, G, n_fixed);       // (only that path multiplies the embedding table on the tensor cores)
-        SH_LAUNCH("gnn_param_bounds", st, param_bounds_kernel<<<dim3(16, p->num_layers + (wide_tables ? 1 : 0)), 256, 0, st>>>(pp, D, b.amax));
+        pp.emb = p->embedding; pp.fc = p->fc_w; pp.emb_n = (long long)(p->num_codes + 1) * D; pp.layers = p->num_layers;
+        const bool wide_tables = D > G_BN && wide_fused(p, G, n_fixed);       // (only that path multiplies the table / fc on the tensor cores)
+        SH_LAUNCH("gnn_param_bounds", st, param_bounds_kernel<<<dim3(wide_tables ? 64 : 16, p->num_layers + (wide_tables ? 2 : 0)), 256, 0, st>>>(pp, D, b.amax));
         SH_CHECK_LAUNCH();
     }
     if (wide_fused(p, G, n_fixed)) {
@@ -1565,6 +1586,24 @@ static int tables_join(const sh_gnn_params *p, int G, int n_fixed, cudaStream_t 
     return 0;
 }
 
+// pooled[g, d] = (sum over chunks of partial[g, chunk, d]) / N   (gnn.py:96: mean over the padded length), + its maximum
+__global__ void __launch_bounds__(256)
+pool_finish_kernel(const float *__restrict__ partial, int chunks, int D, int n_fixed, const int32_t *__restrict__ mean_div,
+                   float *__restrict__ pooled, unsigned *amax)
+{
+    const int g = blockIdx.x;
+    const float div = (float)(mean_div ? *mean_div : n_fixed);
+    float mx = 0.0f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.0f;
+        for (int c = 0; c < chunks; ++c) acc += partial[((size_t)g * chunks + c) * D + d];
+        acc /= div;
+        pooled[(size_t)g * D + d] = acc;
+        mx = fmaxf(mx, fabsf(acc));
+    }
+    record_amax(amax, mx);
+}
+
 // embed_dim > 256 with the layer-0 shortcut (wide_fused).  Per layer l (z_l = the pre-LayerNorm activations):
 //   l = 0:  z_0 = Adj (P_0 rows) + b_0                                  one adjacency GEMM, epilogue stores z_0 (+ tile statistics)
 //   l > 0:  Y = Adj relu(LN_{l-1}(z_{l-1}))                             adjacency GEMM, LayerNorm + ReLU applied to the B operand by the
@@ -1573,7 +1612,7 @@ static int tables_join(const sh_gnn_params *p, int G, int n_fixed, cudaStream_t 
 // z is stored transposed (the next adjacency GEMM's K-major B operand) except for the last layer (rows, for the pooling).
 static int run_layers_wide(const sh_gnn_params *p, int G, int n_fixed, const int32_t *k_sizes, int identity_tail,
                            const int32_t *row_sizes, const float *vertex_w, int ld_v, const TcBuffers &b, int chunks, float *partial,
-                           cudaStream_t st)
+                           cudaStream_t st, TcFinal *fin)
 {
     const int D = p->embed_dim, ldk = b.ldk, nt = D / G_BN, L = p->num_layers;
     const int64_t rows = (int64_t)G * n_fixed;
@@ -1627,6 +1666,23 @@ static int run_layers_wide(const sh_gnn_params *p, int G, int n_fixed, const int
     SH_LAUNCH("gnn_pool_ln_rows", st, pool_ln_rows_kernel<<<grid, 256, 0, st>>>(b.h_rows, b.mr, p->ln_w[L - 1], p->ln_b[L - 1], vertex_w, ld_v,
                                                                                 row_sizes, n_fixed, D, chunks, partial));
     SH_CHECK_LAUNCH();
+    if (fin != nullptr && G >= 64) {
+        // out = fc(pooled / N)  (gnn.py:96-97) as one more tensor-core GEMM: [G, D] x fc_w^T (a CTA per graph re-reading the
+        // D x D weights, pool_fc_kernel, costs 0.4 ms at G = 1000, D = 1024)
+        SH_LAUNCH("gnn_pool_finish", st, pool_finish_kernel<<<G, 256, 0, st>>>(partial, chunks, D, n_fixed, fin->mean_div, b.y, b.amax + AM_POOL));
+        SH_CHECK_LAUNCH();
+        SH_REQUIRE(((uintptr_t)p->fc_w & 15) == 0, "gnn: fc weights must be 16-byte aligned for TMA");
+        CUtensorMap pm, fm, fm2;
+        if (tmap3(&pm, b.y, D, (uint64_t)G, 1, D, 0, G_BM)) return 1;
+        if (tmap3(&fm, p->fc_w, D, D, 1, D, 0, G_BN)) return 1;
+        if (tmap3(&fm2, p->fc_w, D, D, 1, D, 0, G_BN / 2)) return 1;
+        GemmTcArgs c{};
+        c.G = 1; c.rows_per_graph = G; c.M_total = G; c.K_total = D; c.N_total = D; c.batched_b = 0;
+        c.bias = p->fc_b; c.out_rows = fin->out; c.amax_a = b.amax + AM_POOL; c.amax_b = b.amax + AM_FC;
+        CUtensorMap m[2] = {pm, fm}, mp[2] = {pm, fm2};
+        if (launch_gemm3x<EPI_BIAS_ROWS>(m, mp, c, "gnn_fc_tc", st)) return 1;
+        fin->done = true;
+    }
     return 0;
 }
 
@@ -1642,7 +1698,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     // single adjacency GEMM with bias + LayerNorm + ReLU fused in its epilogue.  The table product is staged in the
     // `tab` buffer (as large as Y), which it fits whenever the batch has at least M+1 node slots.
     if (wide_fused(p, G, n_fixed))
-        return run_layers_wide(p, G, n_fixed, k_sizes, identity_tail, row_sizes, vertex_w, ld_v, b, chunks, partial, st);
+        return run_layers_wide(p, G, n_fixed, k_sizes, identity_tail, row_sizes, vertex_w, ld_v, b, chunks, partial, st, fin);
     const bool fuse0 = layer0_fused(p, G, n_fixed);
     SH_REQUIRE(!table_tail || (fuse0 && row_sizes && !identity_tail), "run_layers_tc: table tail needs the fused layer 0");
     const float *table = fuse0 ? b.tab : p->embedding;
@@ -1830,6 +1886,35 @@ int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc
         SH_CHECK_LAUNCH();
     }
     return class_layers_tc(p, K, Vc, b, chunks, partial, st, fin);
+}
+
+// Inner-product logits [B, K] = feat_instance [B, D] . feat_class [K, D]^T (match.py:29-31) as one tensor-core GEMM; K need not
+// be a multiple of the 256-column tile (TMA zero-fills the missing class rows, the epilogue stores the columns that exist).
+// scratch: 2 amax slots.
+bool similarity_tc_supported(int B, int K, int D)
+{
+    return D % G_BK == 0 && D >= 64 && (int64_t)B * K * D >= (1LL << 27) && encode_tiled_fn() != nullptr;
+}
+
+int similarity_tc(const float *fi, const float *fk, int B, int K, int D, float *logits, unsigned *scratch, cudaStream_t st)
+{
+    SH_REQUIRE((((uintptr_t)fi | (uintptr_t)fk) & 15) == 0, "similarity: features must be 16-byte aligned for TMA");
+    SH_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 8, st));
+    SH_LAUNCH("similarity_absmax", st, absmax_kernel<<<32, 256, 0, st>>>(fi, (int64_t)B * D, scratch));
+    SH_CHECK_LAUNCH();
+    SH_LAUNCH("similarity_absmax", st, absmax_kernel<<<32, 256, 0, st>>>(fk, (int64_t)K * D, scratch + 1));
+    SH_CHECK_LAUNCH();
+    const int n_pad = (K + G_BN - 1) / G_BN * G_BN;
+    CUtensorMap am, bm, bm2;
+    if (tmap3(&am, fi, D, (uint64_t)B, 1, D, 0, G_BM)) return 1;
+    if (tmap3(&bm, fk, D, (uint64_t)K, 1, D, 0, G_BN)) return 1;
+    if (tmap3(&bm2, fk, D, (uint64_t)K, 1, D, 0, G_BN / 2)) return 1;
+    GemmTcArgs c{};
+    c.G = 1; c.rows_per_graph = B; c.M_total = B; c.K_total = D; c.N_total = n_pad; c.n_valid = K; c.batched_b = 0;
+    c.out_rows = logits; c.amax_a = scratch; c.amax_b = scratch + 1;
+    SH_REQUIRE(n_pad <= kMaxDim, "similarity: more than %d classes on the tensor-core path", kMaxDim);
+    CUtensorMap m[2] = {am, bm}, mp[2] = {am, bm2};
+    return launch_gemm3x<EPI_BIAS_ROWS>(m, mp, c, "similarity_tc", st);
 }
 
 }  // namespace sh

@@ -31,6 +31,11 @@ int gnn_class_side_tc(const sh_gnn_params *p, float *edge_weights, int K, int Vc
                       const int64_t *class_ingredients, int chunks, float *partial, void *workspace, cudaStream_t st,
                       TcFinal *fin = nullptr);
 
+// Inner-product logits on the tensor cores (large B * K * D only); scratch: 8 bytes of device memory
+bool similarity_tc_supported(int B, int K, int D);
+int similarity_tc(const float *feat_instance, const float *feat_class, int B, int K, int D, float *logits, unsigned *scratch,
+                  cudaStream_t st);
+
 // atlas.cu
 int launch_class_vertices(const float *vertex_weights, int K, int Vc, float *class_vertices, cudaStream_t st);
 int launch_class_edges(float *edge_weights, const float *class_vertices, int K, int Vc, float prune_threshold,

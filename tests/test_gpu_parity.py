@@ -486,6 +486,23 @@ def test_gnn_and_similarity_vs_oracle():
         rel_close(mm.similarity(want.cuda(), fk.cuda()), ref, what=kind)
 
 
+@pytest.mark.parametrize("B,K,D", [(256, 1000, 1024), (2048, 101, 1024), (700, 257, 768)])
+def test_similarity_tensor_core_path(B, K, D):
+    """ImageNet-scale inner-product logits run as one tensor-core GEMM (three fp16 MMAs per product); K is not a multiple of
+    the 256-column tile nor of 4 in two of the cases (ragged output rows)."""
+    from schemanet_b200 import native
+    gen = torch.Generator().manual_seed(B + K)
+    fi = torch.randn(B, D, generator=gen) * 3.0
+    fk = torch.randn(K, D, generator=gen) * 0.5 + 0.1
+    want = (fi.double() @ fk.double().t()).float()
+    got = native.similarity(fi.cuda(), fk.cuda(), "inner_product")
+    assert got.shape == (B, K)
+    rel_close(got, want, what="logits on the tensor cores")
+    # against the one-warp-per-pair kernel on a corner of the problem (same definition, fp32 accumulation)
+    small = native.similarity(fi[:8].cuda(), fk[:16].contiguous().cuda(), "inner_product")
+    rel_close(got[:8, :16], small, what="tensor-core vs CUDA-core logits")
+
+
 def test_class_side_large_tile_path():
     """Vc >= 256 takes the 128x128 GEMM tiles; also exercises Vc that is not a multiple of the tile."""
     from schema_inference.graph import Matcher
