@@ -419,16 +419,20 @@ def run_extra_config(name, args, rank, world, dev, barrier, native):
         other = (rank + 1) % world
         k0 = other * per
         k1 = min(k0 + 2, c["K"])
-        ok = torch.tensor([1], device=dev)
         if k1 > k0:
             sn, gm = head.schema_net, head.matcher.gnn
             _, _, f = native.class_side(gm.param_pack(), sn.vertex_weights.tensor[k0:k1], sn.edge_weights.tensor[k0:k1],
                                         sn.class_ingredients.tensor[k0:k1].contiguous(), sn.prune_node_threshold, True,
                                         sn.remove_self_loop, want_edges=not native.gnn_tensor_path(c["D"], c["Vc"]))
-            ok = torch.tensor([1 if torch.equal(f, out["feat_class"][k0:k1]) else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        sub["class_shard_check"] = ("rows gathered from the next rank == the same classes recomputed locally (bit-identical) on "
-                                    "every rank") if int(ok) == 1 else "MISMATCH"
+            g_rows = out["feat_class"][k0:k1]
+            ok = torch.tensor([float((f - g_rows).abs().max() / g_rows.abs().max().clamp_min(1e-30))], device=dev)
+        else:
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MAX)
+        # (a call on 2 classes may take another kernel path than the shard's -- e.g. no layer-0 table shortcut when there are
+        # fewer node slots than codes -- and operand scales depend on the graphs of the call: compared to 1e-5, not bit for bit)
+        sub["class_shard_check"] = {"what": "rows gathered from the next rank vs the same classes recomputed locally, worst rank",
+                                    "max_rel": float(ok), "ok": bool(float(ok) <= 1e-5)}
     del graphed, head, sets, schema
     torch.cuda.empty_cache()
     return sub if rank == 0 else None

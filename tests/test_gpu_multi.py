@@ -40,18 +40,43 @@ def _worker(rank, world, port):
         sn, m = build_modules(schema=schema, gnn=gnn, M=M, K=K, Vc=Vc, D=D, dev=dev)
         lo, hi = shdist.shard_range(B, rank, world)          # batch shard of this rank
         mid_s, attn_s, cls_s = mid[:, lo:hi].contiguous().to(dev), attn[lo:hi].to(dev), attn_cls[lo:hi].to(dev)
+        # every check is recorded and reduced over the ranks before anything is raised: a rank that raised alone would leave its
+        # peer waiting in the next collective
+        problems = []
+
+        def rel(a, b):
+            return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
         full = SchemaHead(vocab.to(dev), sn, m)(mid_s, attn_s, cls_s)
         shard = SchemaHead(vocab.to(dev), sn, m, class_shard=(rank, world))(mid_s, attn_s, cls_s)
-        assert torch.equal(shard["feat_class"], full["feat_class"]), "class embeddings differ under class sharding"
-        assert torch.equal(shard["pred"], full["pred"])
+        # (not bit-identical: the GEMM operand scales are powers of two taken from the maxima of the graphs a call processes, and
+        # a different grouping of the class graphs moves which tiny entries fall into fp16 subnormals -- ~1e-7 relative)
+        if rel(shard["feat_class"], full["feat_class"]) > 1e-6:
+            problems.append(f"class embeddings differ under class sharding: {rel(shard['feat_class'], full['feat_class']):.2e}")
+        if rel(shard["pred"], full["pred"]) > 1e-6:
+            problems.append(f"logits differ under class sharding: {rel(shard['pred'], full['pred']):.2e}")
         ref = ho.head_forward(mid[:, lo:hi].contiguous(), attn[lo:hi], attn_cls[lo:hi], vocab, schema, gnn, ho.HEAD_CFG)
         err = (shard["pred"].cpu() - ref["pred"]).abs().max() / ref["pred"].abs().max()
-        assert err < 1e-5, f"rank {rank}: logits rel err {err:.2e}"
+        if not err < 1e-5:
+            problems.append(f"rank {rank}: logits rel err {err:.2e}")
+        # the class-sharded step as ONE CUDA graph (the NCCL all-gather is captured on the class-side stream); replay == eager
+        from schemanet_b200.head import GraphedHead
+        head_g = SchemaHead(vocab.to(dev), sn, m, class_shard=(rank, world))
+        gh = GraphedHead(head_g, mid_s.clone(), attn_s.clone(), cls_s.clone())
+        for _ in range(3):
+            out_g = gh.replay()
+        torch.cuda.synchronize()
+        if not torch.equal(out_g["pred"], shard["pred"]):
+            problems.append("graph replay of the class-sharded head differs from the eager result")
         mv = shard["graphs"].max_vertices.clone()
         shdist.global_max_vertices(mv)
         sizes = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
         dist.all_gather(sizes, shard["graphs"].max_vertices)
-        assert int(mv) == max(int(s) for s in sizes)
+        if int(mv) != max(int(s) for s in sizes):
+            problems.append("global_max_vertices")
+        bad = torch.tensor([len(problems)], device=dev)
+        dist.all_reduce(bad)
+        assert int(bad) == 0, f"rank {rank}: {problems or 'a peer rank failed'}"
     finally:
         dist.destroy_process_group()
 
