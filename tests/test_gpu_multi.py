@@ -47,7 +47,12 @@ def _worker(rank, world, port):
         def rel(a, b):
             return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
+        def mark(msg):
+            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+        dist.barrier()                                       # (communicator up before the first collective on a side stream)
         full = SchemaHead(vocab.to(dev), sn, m)(mid_s, attn_s, cls_s)
+        torch.cuda.synchronize(); mark("full head done")
         shard = SchemaHead(vocab.to(dev), sn, m, class_shard=(rank, world))(mid_s, attn_s, cls_s)
         # (not bit-identical: the GEMM operand scales are powers of two taken from the maxima of the graphs a call processes, and
         # a different grouping of the class graphs moves which tiny entries fall into fp16 subnormals -- ~1e-7 relative)
@@ -55,6 +60,7 @@ def _worker(rank, world, port):
             problems.append(f"class embeddings differ under class sharding: {rel(shard['feat_class'], full['feat_class']):.2e}")
         if rel(shard["pred"], full["pred"]) > 1e-6:
             problems.append(f"logits differ under class sharding: {rel(shard['pred'], full['pred']):.2e}")
+        torch.cuda.synchronize(); mark("sharded head done")
         ref = ho.head_forward(mid[:, lo:hi].contiguous(), attn[lo:hi], attn_cls[lo:hi], vocab, schema, gnn, ho.HEAD_CFG)
         err = (shard["pred"].cpu() - ref["pred"]).abs().max() / ref["pred"].abs().max()
         if not err < 1e-5:
@@ -63,17 +69,21 @@ def _worker(rank, world, port):
         from schemanet_b200.head import GraphedHead
         head_g = SchemaHead(vocab.to(dev), sn, m, class_shard=(rank, world))
         gh = GraphedHead(head_g, mid_s.clone(), attn_s.clone(), cls_s.clone())
+        mark("graph captured")
         for _ in range(3):
             out_g = gh.replay()
         torch.cuda.synchronize()
         if not torch.equal(out_g["pred"], shard["pred"]):
             problems.append("graph replay of the class-sharded head differs from the eager result")
+        del gh, out_g, head_g            # a live CUDA graph holds NCCL kernels: release it before the communicator goes away
+        torch.cuda.synchronize()
         mv = shard["graphs"].max_vertices.clone()
         shdist.global_max_vertices(mv)
         sizes = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
         dist.all_gather(sizes, shard["graphs"].max_vertices)
         if int(mv) != max(int(s) for s in sizes):
             problems.append("global_max_vertices")
+        mark(f"checks done: {problems}")
         bad = torch.tensor([len(problems)], device=dev)
         dist.all_reduce(bad)
         assert int(bad) == 0, f"rank {rank}: {problems or 'a peer rank failed'}"
