@@ -45,6 +45,7 @@ using namespace tc;
 constexpr int G_BM = 128;
 constexpr int G_BN = 256;      // == embed_dim
 constexpr int G_BK = 32;
+constexpr int kGatherMaxNodes = 1024;                      // node codes of one graph held in shared memory by a gathering GEMM
 constexpr int G_XF_WARPS = 8;                              // operand-transform warps
 constexpr int G_THREADS = 192 + 32 * G_XF_WARPS;
 constexpr int kABytes = G_BM * G_BK * 4;                 // 16 KB
@@ -92,6 +93,15 @@ struct GemmTcArgs {
     // B operand = relu(LayerNorm(z)) of the stored z^T, applied by the transform warps (null: B is used as stored):
     const float *bln_mr;         // [G * rows_per_graph, 2] merged (mean, rstd) per node
     const float *bln_gamma, *bln_beta;   // [N_total]
+    // B operand GATHERED instead of loaded by a tiled TMA (layer 0: X_0^T[f, k] = table[ids[g, k], f], so the [G, D, n] copy of
+    // the gathered table rows is never written): the producer warp issues one bulk copy per node (its slice of a table row,
+    // completing on the stage's mbarrier like a TMA box); the landing tile is [k][f] and the transform warps read it
+    // transposed.  bg_table [rows, N_total] fp32, bg_ids [G, bg_ld] node codes, bg_sizes [G] live nodes per graph (null:
+    // rows_per_graph); nodes beyond read bg_zero_row, a table row that is all zeros (the padding code's)
+    const float *bg_table;
+    const int64_t *bg_ids;
+    const int32_t *bg_sizes;
+    int bg_ld, bg_zero_row;
     int debug;      // timing experiments (SCHEMANET_GEMM_DEBUG): 1 transform skips its work, 2 no MMAs, 4 epilogue skips its work
     long long *trace;   // SCHEMANET_GEMM_TRACE: per CTA 8 cycle counters (see launch_gemm3x_n), null in normal runs
 };
@@ -157,6 +167,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
     return x;
 }
+__device__ __forceinline__ float lds32(uint32_t addr)
+{
+    float x;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
+    return x;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -197,7 +213,8 @@ struct GemmPlan {
     static constexpr int kBar = kStages * kStage;
     static constexpr int kParam = kBar + 256;
     static constexpr int kStageOut = kParam + (2 * G_BN + kMaxDim) * 4;   // gamma, beta (LN: 256 wide) + bias (up to kMaxDim)
-    static constexpr int kTotal = kStageOut + 4 * 32 * 33 * 4 + 1024;
+    static constexpr int kIds = kStageOut + 4 * 32 * 33 * 4;                // node codes of the current graph (gathered B operand)
+    static constexpr int kTotal = kIds + 1024 * 4 + 1024;            // (kGatherMaxNodes int32)
 };
 
 template <int EPI, int CTAS>
@@ -277,7 +294,35 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     long long tr0 = 0, tr1 = 0;                            // (trace: cycles this role spent waiting / working)
     const long long tr_start = a.trace ? clock64() : 0;
     if (warp == 0) {
-        if (lane == 0) {
+        if (a.bg_table != nullptr) {
+            // ===================== producer, gathered B: whole warp =====================
+            int *s_ids = reinterpret_cast<int *>(smem + P::kIds);
+            int stage = 0;
+            uint32_t phase = 0;
+            TILE_LOOP_BEGIN
+                const int n_live = a.bg_sizes ? a.bg_sizes[g] : a.rows_per_graph;
+                __syncwarp();
+                for (int i = lane; i < kGatherMaxNodes; i += 32)          // table row of every node of graph g
+                    s_ids[i] = i < n_live ? (int)a.bg_ids[(size_t)g * a.bg_ld + i] : a.bg_zero_row;
+                __syncwarp();
+                for (int kidx = 0; kidx < kblocks; ++kidx) {
+                    const int kb = kidx < kA ? kidx : k2s + (kidx - kA);
+                    uint8_t *s = smem + stage * P::kStage;
+                    if (lane == 0) {
+                        { TR_T0(); mbar_wait(&empty[stage], phase ^ 1); TR_ADD(tr0); }
+                        mbar_arrive_expect_tx(&full[stage], P::kStage);
+                        tma_load_3d(s, &tmA, &full[stage], kb * G_BK, mb * G_BM, g);
+                    }
+                    __syncwarp();                                           // the slot is free: every lane may write into it
+                    const int k = kb * G_BK + lane;
+                    const int row = k < kGatherMaxNodes ? s_ids[k] : a.bg_zero_row;
+                    const float *src = a.bg_table + (size_t)row * a.N_total + nb * G_BN + rank * P::kBRows;
+                    bulk_copy_g2s(s + kABytes + lane * (P::kBRows * 4), src, P::kBRows * 4, &full[stage]);
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            TILE_LOOP_END
+            if (a.trace && lane == 0) a.trace[blockIdx.x * 8 + 0] = tr0;
+        } else if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             TILE_LOOP_BEGIN
@@ -377,6 +422,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], unscale, s_bias[nb * G_BN + c * 32 + j]);
+                    if (a.amax_out != nullptr && m < a.M_total) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) out_max = fmaxf(out_max, fabsf(v[j]));
+                    }
                     if (a.n_valid == 0) {
                         store_chunk_rows(s_out + wq * 32 * 33, v, lane, o + c * 32, a.N_total, min(32, a.M_total - m_warp));
                     } else if (m < a.M_total) {
@@ -536,7 +585,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
             tc_fence_before();
             __syncwarp();
-            if (EPI == EPI_STORE_ROWS || EPI == EPI_LN_RELU_T) record_amax(a.amax_out, out_max);
+            if (EPI == EPI_STORE_ROWS || EPI == EPI_LN_RELU_T || EPI == EPI_BIAS_ROWS) record_amax(a.amax_out, out_max);
             if (a.trace) tr1 += clock64() - tr_w0;
             if (lane == 0) {
                 if (CTAS == 1) mbar_arrive(&tmem_empty[as]);
@@ -561,8 +610,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         constexpr int kBPer = P::kBRows / 128;                      // B rows per thread
         int stage = 0;
         uint32_t phase = 0;
+        const bool gather = a.bg_table != nullptr;
         TILE_LOOP_BEGIN
-            (void)nb; (void)mb;
+            (void)mb;
             for (int kidx = 0; kidx < kblocks; ++kidx) {
                 { TR_T0(); mbar_wait(&full[stage], phase); TR_ADD(tr0); }     // this CTA's fp32 tiles have landed
                 const long long tr_w0 = a.trace ? clock64() : 0;
@@ -570,11 +620,26 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 float4 va[4], vb[kBPer][4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) va[c] = lds128(sb + (uint32_t)trow * 128u + (((uint32_t)(4 * th + c) ^ swz) << 4));
+                if (!gather) {
 #pragma unroll
-                for (int h = 0; h < kBPer; ++h)
+                    for (int h = 0; h < kBPer; ++h)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        vb[h][c] = lds128(sb + kABytes + (uint32_t)(trow + 128 * h) * 128u + (((uint32_t)(4 * th + c) ^ swz) << 4));
+                        for (int c = 0; c < 4; ++c)
+                            vb[h][c] = lds128(sb + kABytes + (uint32_t)(trow + 128 * h) * 128u + (((uint32_t)(4 * th + c) ^ swz) << 4));
+                } else {
+                    // gathered B: the landing tile is [k][f] (one bulk copy per node): read this thread's 16 nodes of feature row f
+                    // (32 lanes = 32 consecutive f: conflict-free)
+#pragma unroll
+                    for (int h = 0; h < kBPer; ++h)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t base = sb + kABytes + (uint32_t)((16 * th + 4 * c) * (P::kBRows * 4) + (trow + 128 * h) * 4);
+                            vb[h][c].x = lds32(base);
+                            vb[h][c].y = lds32(base + P::kBRows * 4);
+                            vb[h][c].z = lds32(base + 2 * P::kBRows * 4);
+                            vb[h][c].w = lds32(base + 3 * P::kBRows * 4);
+                        }
+                }
                 asm volatile("bar.sync 2, %0;" ::"n"(32 * G_XF_WARPS) : "memory");       // every landing row is in registers
                 if (a.bln_mr != nullptr) {
                     // B holds z^T of the previous layer: h = relu((z - mean_k) rstd_k gamma_f + beta_f) for feature row f, node k
@@ -1231,29 +1296,45 @@ pool_ln_rows_kernel(const float *__restrict__ Z, const float *__restrict__ mr, c
                     const float *__restrict__ beta, const float *__restrict__ vertex_w, int ld_v, const int32_t *__restrict__ sizes,
                     int n_fixed, int D, int chunks, float *__restrict__ partial)
 {
+    // a thread owns 4 consecutive features (one float4 per row: a warp reads 512 contiguous bytes), 4 rows in flight
     const int g = blockIdx.y, chunk = blockIdx.x;
     const int n_g = sizes ? sizes[g] : n_fixed;
     const int per = ceil_div(n_fixed, chunks);
     const int r0 = chunk * per, r1 = min(n_g, r0 + per);
     const float2 *mrg = reinterpret_cast<const float2 *>(mr) + (size_t)g * n_fixed;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        const float gam = gamma[d], bet = beta[d];
-        float acc = 0.0f;
-        for (int r = r0; r < r1; ++r) {
-            const float2 s = mrg[r];
-            const float h = fmaxf(fmaf(Z[((size_t)g * n_fixed + r) * D + d] - s.x, s.y * gam, bet), 0.0f);
-            acc = fmaf(h, vertex_w[(size_t)g * ld_v + r], acc);
+    const float *wg = vertex_w + (size_t)g * ld_v;
+    for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+        const float4 gam = *reinterpret_cast<const float4 *>(gamma + d), bet = *reinterpret_cast<const float4 *>(beta + d);
+        const float *zp = Z + ((size_t)g * n_fixed + r0) * D + d;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int r = r0;
+        for (; r + 4 <= r1; r += 4) {
+            float4 z[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) z[u] = __ldcs(reinterpret_cast<const float4 *>(zp + (size_t)u * D));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {           // rows in ascending order: the sum does not depend on the unrolling
+                const float2 s = mrg[r + u];
+                const float w = wg[r + u];
+                acc.x = fmaf(fmaxf(fmaf(z[u].x - s.x, s.y * gam.x, bet.x), 0.0f), w, acc.x);
+                acc.y = fmaf(fmaxf(fmaf(z[u].y - s.x, s.y * gam.y, bet.y), 0.0f), w, acc.y);
+                acc.z = fmaf(fmaxf(fmaf(z[u].z - s.x, s.y * gam.z, bet.z), 0.0f), w, acc.z);
+                acc.w = fmaf(fmaxf(fmaf(z[u].w - s.x, s.y * gam.w, bet.w), 0.0f), w, acc.w);
+            }
+            zp += (size_t)4 * D;
         }
-        partial[((size_t)g * chunks + chunk) * D + d] = acc;
+        for (; r < r1; ++r) {
+            const float4 z = __ldcs(reinterpret_cast<const float4 *>(zp));
+            const float2 s = mrg[r];
+            const float w = wg[r];
+            acc.x = fmaf(fmaxf(fmaf(z.x - s.x, s.y * gam.x, bet.x), 0.0f), w, acc.x);
+            acc.y = fmaf(fmaxf(fmaf(z.y - s.x, s.y * gam.y, bet.y), 0.0f), w, acc.y);
+            acc.z = fmaf(fmaxf(fmaf(z.z - s.x, s.y * gam.z, bet.z), 0.0f), w, acc.z);
+            acc.w = fmaf(fmaxf(fmaf(z.w - s.x, s.y * gam.w, bet.w), 0.0f), w, acc.w);
+            zp += D;
+        }
+        *reinterpret_cast<float4 *>(partial + ((size_t)g * chunks + chunk) * D + d) = acc;
     }
-}
-
-// max |x| of a small tensor into an amax slot
-__global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x, int64_t n, unsigned *slot)
-{
-    float mx = 0.0f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mx = fmaxf(mx, fabsf(__ldg(x + i)));
-    record_amax(slot, mx);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1534,11 +1615,15 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
         GemmTcArgs c{};
         c.G = 1; c.rows_per_graph = rows; c.M_total = rows; c.K_total = D; c.N_total = D; c.batched_b = 0;
         c.out_rows = b.tab; c.amax_a = b.amax + AM_EMB; c.amax_b = b.amax + AM_W;
+        c.amax_out = b.amax + AM_X;        // the largest table entry bounds every gathered X_0 entry
         CUtensorMap m[2] = {em, wm}, mp[2] = {em, wm2};
         if (launch_gemm3x<EPI_BIAS_ROWS>(m, mp, c, "gnn_embed_table_tc", st)) return 1;
-        dim3 grid2(ceil_div(b.ldk, 32), ceil_div(D, 256), G);
-        SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(b.tab, ids, ld_ids, row_sizes, n_fixed, b.ldk, D, b.xt, b.amax + AM_X));
-        SH_CHECK_LAUNCH();
+        if (n_fixed > kGatherMaxNodes) {      // (the in-GEMM gather keeps a graph's node codes in shared memory)
+            dim3 grid2(ceil_div(b.ldk, 32), ceil_div(D, 256), G);
+            SH_LAUNCH("gnn_embed_gather", st, embed_gather_t_kernel<<<grid2, 256, 0, st>>>(b.tab, ids, ld_ids, row_sizes, n_fixed, b.ldk, D, b.xt, b.amax + AM_X));
+            SH_CHECK_LAUNCH();
+        }
+        // otherwise no gather kernel: the layer-0 adjacency GEMM reads the table rows itself (run_layers_wide)
         return 0;
     }
     if (!layer0_fused(p, G, n_fixed)) return 0;
@@ -1611,8 +1696,8 @@ pool_finish_kernel(const float *__restrict__ partial, int chunks, int D, int n_f
 //   end:    pooled = sum_i relu(LN_{L-1}(z_{L-1}))_i w_i                 pool_ln_rows_kernel, straight from the z rows
 // z is stored transposed (the next adjacency GEMM's K-major B operand) except for the last layer (rows, for the pooling).
 static int run_layers_wide(const sh_gnn_params *p, int G, int n_fixed, const int32_t *k_sizes, int identity_tail,
-                           const int32_t *row_sizes, const float *vertex_w, int ld_v, const TcBuffers &b, int chunks, float *partial,
-                           cudaStream_t st, TcFinal *fin)
+                           const int32_t *row_sizes, const int64_t *ids, int ld_ids, const float *vertex_w, int ld_v, const TcBuffers &b,
+                           int chunks, float *partial, cudaStream_t st, TcFinal *fin)
 {
     const int D = p->embed_dim, ldk = b.ldk, nt = D / G_BN, L = p->num_layers;
     const int64_t rows = (int64_t)G * n_fixed;
@@ -1637,6 +1722,10 @@ static int run_layers_wide(const sh_gnn_params *p, int G, int n_fixed, const int
         a.amax_a = b.amax + AM_ADJ; a.ldk = ldk; a.stats = b.stats; a.eps = p->ln_eps;
         if (l == 0) {
             a.amax_b = b.amax + AM_X; a.row_sizes = row_sizes; a.bias = p->lin_b[0];
+            if (n_fixed <= kGatherMaxNodes) {     // B = rows of the table P_0 gathered by node code inside the GEMM
+                a.bg_table = b.tab; a.bg_ids = ids; a.bg_ld = ld_ids; a.bg_sizes = row_sizes;
+                a.bg_zero_row = p->num_codes;          // Emb[num_codes] = 0 (padding_idx, gnn.py:66-70) -> P_0[num_codes] = 0
+            }
             if (last) { a.out_rows = b.h_rows; if (launch_gemm3x<EPI_Z_ROWS_STATS>(m1, m1p, a, "gnn_adj_z_tc", st)) return 1; }
             else { a.out_t = xout; if (launch_gemm3x<EPI_Z_T_STATS>(m1, m1p, a, "gnn_adj_z_tc", st)) return 1; }
             if (merge()) return 1;
@@ -1698,7 +1787,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     // single adjacency GEMM with bias + LayerNorm + ReLU fused in its epilogue.  The table product is staged in the
     // `tab` buffer (as large as Y), which it fits whenever the batch has at least M+1 node slots.
     if (wide_fused(p, G, n_fixed))
-        return run_layers_wide(p, G, n_fixed, k_sizes, identity_tail, row_sizes, vertex_w, ld_v, b, chunks, partial, st, fin);
+        return run_layers_wide(p, G, n_fixed, k_sizes, identity_tail, row_sizes, ids, ld_ids, vertex_w, ld_v, b, chunks, partial, st, fin);
     const bool fuse0 = layer0_fused(p, G, n_fixed);
     SH_REQUIRE(!table_tail || (fuse0 && row_sizes && !identity_tail), "run_layers_tc: table tail needs the fused layer 0");
     const float *table = fuse0 ? b.tab : p->embedding;

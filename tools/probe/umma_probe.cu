@@ -4,6 +4,9 @@
 //   variant 0: SWIZZLE_NONE, K-major "interleaved": core matrix = 8 rows x 16 B contiguous; LBO = stride between the two
 //              16-byte k-chunks of one K=16 step, SBO = stride between 8-row groups  (cute::UMMA make_umma_desc<Major::K>)
 //   variant 1: SWIZZLE_64B, K-major: rows of 64 B (32 halves), 16-byte chunk c of row r stored at c ^ ((r >> 1) & 3)
+//   variant 2: A as variant 0; B MN-major "interleaved" (instruction descriptor bit 16 = 1): a 16-byte chunk holds 8
+//              consecutive N elements of one k; 8 consecutive k are contiguous (128 B core matrix); SBO = stride between
+//              N chunks, LBO = stride between groups of 8 k.  B is given as [K][N] (k rows) in global memory.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -o umma_probe umma_probe.cu
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -31,7 +34,7 @@ __device__ __forceinline__ uint32_t chunk_off(int variant, int r, int c)
     return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) * 16));
 }
 
-__global__ void __launch_bounds__(128) probe(const __half *A, const __half *B, float *D, int variant)
+__global__ void __launch_bounds__(128) probe(const __half *A, const __half *B, const __half *Bt, float *D, int variant)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -43,9 +46,17 @@ __global__ void __launch_bounds__(128) probe(const __half *A, const __half *B, f
         const int r = i / 4, c = i % 4;
         *reinterpret_cast<uint4 *>(sA + chunk_off(variant, r, c)) = *reinterpret_cast<const uint4 *>(A + r * K + c * 8);
     }
-    for (int i = tid; i < N * 4; i += 128) {
-        const int r = i / 4, c = i % 4;
-        *reinterpret_cast<uint4 *>(sB + chunk_off(variant, r, c)) = *reinterpret_cast<const uint4 *>(B + r * K + c * 8);
+    if (variant < 2) {
+        for (int i = tid; i < N * 4; i += 128) {
+            const int r = i / 4, c = i % 4;
+            *reinterpret_cast<uint4 *>(sB + chunk_off(variant, r, c)) = *reinterpret_cast<const uint4 *>(B + r * K + c * 8);
+        }
+    } else {
+        // Bt [K][N]: chunk (k, n8) = Bt[k][8 n8 .. 8 n8 + 7] -> (k % 8) * 16 + n8 * 128 + (k / 8) * (N / 8) * 128
+        for (int i = tid; i < K * (N / 8); i += 128) {
+            const int k = i % K, n8 = i / K;
+            *reinterpret_cast<uint4 *>(sB + (k % 8) * 16 + n8 * 128 + (k / 8) * (N / 8) * 128) = *reinterpret_cast<const uint4 *>(Bt + k * N + n8 * 8);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (tid == 0) {
@@ -66,13 +77,19 @@ __global__ void __launch_bounds__(128) probe(const __half *A, const __half *B, f
             if (variant == 0) {       // K step k = chunks 2k, 2k+1: start at +256 B per step, LBO = 128, SBO = 512
                 da = desc(smem_u32(sA) + k * 256, 128, 512, 0);
                 db = desc(smem_u32(sB) + k * 256, 128, 512, 0);
-            } else {                  // 64-byte swizzle: +32 B per K step, SBO = 8 rows x 64 B
+            } else if (variant == 2) { // B MN-major: a K = 16 step = 2 groups of 8 k, LBO = (N / 8) * 128 apart; SBO = 128
+                da = desc(smem_u32(sA) + k * 256, 128, 512, 0);
+                db = desc(smem_u32(sB) + k * 2 * (N / 8) * 128, (N / 8) * 128, 128, 0);
+            } else if (variant == 3) { // same layout, LBO / SBO exchanged
+                da = desc(smem_u32(sA) + k * 256, 128, 512, 0);
+                db = desc(smem_u32(sB) + k * 2 * (N / 8) * 128, 128, (N / 8) * 128, 0);
+            } else {                  // (variant 1) 64-byte swizzle: +32 B per K step, SBO = 8 rows x 64 B
                 da = desc(smem_u32(sA) + k * 32, 16, 512, 4);
                 db = desc(smem_u32(sB) + k * 32, 16, 512, 4);
             }
             const uint32_t acc = k != 0;
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                         ::"r"(tmem), "l"(da), "l"(db), "r"(idesc_f16(M, N)), "r"(acc) : "memory");
+                         ::"r"(tmem), "l"(da), "l"(db), "r"(idesc_f16(M, N) | (variant >= 2 ? (1u << 16) : 0u)), "r"(acc) : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
     }
@@ -119,22 +136,25 @@ int main()
             for (int k = 0; k < K; ++k) s += __half2float(hA[m * K + k]) * __half2float(hB[n * K + k]);
             ref[m * N + n] = s;
         }
-    __half *dA, *dB;
+    __half *dA, *dB, *dBt;
     float *dD;
-    cudaMalloc(&dA, M * K * 2); cudaMalloc(&dB, N * K * 2); cudaMalloc(&dD, M * N * 4);
+    __half *hBt = (__half *)malloc(N * K * 2);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) hBt[k * N + n] = hB[n * K + k];
+    cudaMalloc(&dA, M * K * 2); cudaMalloc(&dB, N * K * 2); cudaMalloc(&dBt, N * K * 2); cudaMalloc(&dD, M * N * 4);
     cudaMemcpy(dA, hA, M * K * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hB, N * K * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(dBt, hBt, N * K * 2, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960);
-    for (int variant = 0; variant < 2; ++variant) {
+    for (int variant = 0; variant < 4; ++variant) {
         cudaMemset(dD, 0, M * N * 4);
-        probe<<<1, 128, 40960>>>(dA, dB, dD, variant);
+        probe<<<1, 128, 40960>>>(dA, dB, dBt, dD, variant);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("variant %d: CUDA error %s\n", variant, cudaGetErrorString(e)); return 1; }
         cudaMemcpy(out, dD, M * N * 4, cudaMemcpyDeviceToHost);
         double worst = 0;
         int bad = 0;
         for (int i = 0; i < M * N; ++i) { double d = fabs(out[i] - ref[i]); if (d > worst) worst = d; if (d > 1e-3) ++bad; }
-        printf("variant %d (%s): max |err| = %g, wrong entries = %d / %d\n", variant, variant == 0 ? "SWIZZLE_NONE LBO=128 SBO=512" : "SWIZZLE_64B SBO=512", worst, bad, M * N);
+        printf("variant %d (%s): max |err| = %g, wrong entries = %d / %d\n", variant, variant == 0 ? "SWIZZLE_NONE LBO=128 SBO=512" : (variant == 1 ? "SWIZZLE_64B SBO=512" : (variant == 2 ? "B MN-major interleaved LBO=kgroup SBO=nchunk" : "B MN-major interleaved LBO=nchunk SBO=kgroup")), worst, bad, M * N);
     }
     return 0;
 }
