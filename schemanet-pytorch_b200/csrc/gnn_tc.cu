@@ -1337,6 +1337,14 @@ pool_ln_rows_kernel(const float *__restrict__ Z, const float *__restrict__ mr, c
     }
 }
 
+// max |x| of a small tensor into an amax slot
+__global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x, int64_t n, unsigned *slot)
+{
+    float mx = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mx = fmaxf(mx, fabsf(__ldg(x + i)));
+    record_amax(slot, mx);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------------
