@@ -46,8 +46,14 @@ constexpr int G_BM = 128;
 constexpr int G_BN = 256;      // == embed_dim
 constexpr int G_BK = 32;
 constexpr int kGatherMaxNodes = 1024;                      // node codes of one graph held in shared memory by a gathering GEMM
+// Warp budget (448 threads, 128 registers each).  Measured on B200 (profiles/r02_experiments.md): 4 epilogue + 8 transform warps
+// and 8 + 4 give the same cfg2 step (0.675 / 0.679 ms) -- the second epilogue warpgroup shortens the exposed last epilogue, the
+// 4-warp conversion (64 live floats per thread, spills) gives it back -- and 8 + 4 is 4 % slower at cfg4, where the transform
+// also applies LayerNorm.  G_EPI_WARPS = 8: two warps per TMEM lane quarter, each owns half of a tile's columns.
+constexpr int G_EPI_WARPS = 4;
 constexpr int G_XF_WARPS = 8;                              // operand-transform warps
-constexpr int G_THREADS = 192 + 32 * G_XF_WARPS;
+constexpr int G_XF_FIRST = 2 + G_EPI_WARPS;                // first transform warp
+constexpr int G_THREADS = 32 * (G_XF_FIRST + G_XF_WARPS);
 constexpr int kABytes = G_BM * G_BK * 4;                 // 16 KB
 
 enum { EPI_STORE_ROWS = 0, EPI_LN_RELU_T = 1, EPI_LN_RELU_ROWS = 2, EPI_BIAS_ROWS = 3,
@@ -209,11 +215,12 @@ struct GemmPlan {
     static constexpr int kBBytesL = kBRows * G_BK * 4;            // landing bytes of the B rows = hi tile + lo tile
     static constexpr int kBTile = kBBytesL / 2;
     static constexpr int kStage = kABytes + kBBytesL;
-    static constexpr int kStages = CTAS == 1 ? 4 : 6;
+    static constexpr int kStages = G_EPI_WARPS == 4 ? (CTAS == 1 ? 4 : 6) : (CTAS == 1 ? 3 : 5);
     static constexpr int kBar = kStages * kStage;
     static constexpr int kParam = kBar + 256;
     static constexpr int kStageOut = kParam + (2 * G_BN + kMaxDim) * 4;   // gamma, beta (LN: 256 wide) + bias (up to kMaxDim)
-    static constexpr int kIds = kStageOut + 4 * 32 * 33 * 4;                // node codes of the current graph (gathered B operand)
+    static constexpr int kXch = kStageOut + G_EPI_WARPS * 32 * 33 * 4;      // LayerNorm partials exchanged by the two column halves
+    static constexpr int kIds = kXch + 2 * 2 * G_BM * 8;                    // node codes of the current graph (gathered B operand)
     static constexpr int kTotal = kIds + 1024 * 4 + 1024;            // (kGatherMaxNodes int32)
 };
 
@@ -251,7 +258,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], G_XF_WARPS * CTAS); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * CTAS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], G_EPI_WARPS * CTAS); }
         fence_barrier_init();
     }
     if (CTAS == 2) cluster_sync();       // the peer's barriers must exist before anything signals them
@@ -385,9 +392,25 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             TILE_LOOP_END
             if (a.trace && lane == 0) { a.trace[blockIdx.x * 8 + 3] = tr0; a.trace[blockIdx.x * 8 + 4] = tr1; }
         }
-    } else if (warp < 6) {
+    } else if (warp < G_XF_FIRST) {
+        // ===================== epilogue: two warps per TMEM lane quarter, each owns half of the tile's 8 column chunks =====================
         const int wq = warp & 3;
+        constexpr int kCPW = (G_BN / 32) / (G_EPI_WARPS / 4);                   // column chunks per warp
+        const int half = (warp - 2) >> 2;
+        const int c_lo = half * kCPW, c_hi = c_lo + kCPW;
         const int row_in_tile = wq * 32 + lane;
+        float *s_tile = s_out + (wq + 4 * half) * 32 * 33;                     // this warp's staging tile
+        float2 *s_xch = reinterpret_cast<float2 *>(smem + P::kXch);             // [accumulator][half][row]: (mean, M2) of a half row
+        // the two warps of a quarter combine their halves' statistics (equal counts n = 128: Chan et al.)
+        auto combine_halves = [&](int as_, float mean_h, float m2_h, float &mean, float &m2) {
+            if (G_EPI_WARPS == 4) { mean = mean_h; m2 = m2_h; return; }          // one warp owns the whole row
+            s_xch[(as_ * 2 + half) * G_BM + row_in_tile] = make_float2(mean_h, m2_h);
+            asm volatile("bar.sync %0, 64;" ::"r"(3 + wq) : "memory");
+            const float2 o = s_xch[(as_ * 2 + (half ^ 1)) * G_BM + row_in_tile];
+            const float dlt = mean_h - o.x;
+            mean = 0.5f * (mean_h + o.x);
+            m2 = m2_h + o.y + (float)(G_BN / 4) * dlt * dlt;
+        };
         int as = 0;
         uint32_t aphase = 0;
         TILE_LOOP_BEGIN
@@ -405,19 +428,19 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 const int rows_valid = min(32, a.rows_per_graph - m_warp);
                 float *o = a.out_rows + ((size_t)g * a.rows_per_graph + m_warp) * a.N_total + nb * G_BN;
 #pragma unroll 1
-                for (int c = 0; c < G_BN / 32; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { v[j] *= unscale; out_max = fmaxf(out_max, fabsf(v[j])); }
-                    store_chunk_rows(s_out + wq * 32 * 33, v, lane, o + c * 32, a.N_total, rows_valid);
+                    store_chunk_rows(s_tile, v, lane, o + c * 32, a.N_total, rows_valid);
                 }
             } else if (EPI == EPI_BIAS_ROWS) {
                 // Z[m, nb*256 + :] = acc + bias (embed_dim > 256: LayerNorm needs the whole row and runs as its own kernel)
                 const int m_warp = mb * G_BM + wq * 32;
                 float *o = a.out_rows + (size_t)m_warp * a.N_total + nb * G_BN;
 #pragma unroll 1
-                for (int c = 0; c < G_BN / 32; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
@@ -427,7 +450,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         for (int j = 0; j < 32; ++j) out_max = fmaxf(out_max, fabsf(v[j]));
                     }
                     if (a.n_valid == 0) {
-                        store_chunk_rows(s_out + wq * 32 * 33, v, lane, o + c * 32, a.N_total, min(32, a.M_total - m_warp));
+                        store_chunk_rows(s_tile, v, lane, o + c * 32, a.N_total, min(32, a.M_total - m_warp));
                     } else if (m < a.M_total) {
                         // ragged output width (logits [B, K]): this thread's row, the columns that exist
                         float *orow = a.out_rows + (size_t)m * a.n_valid + nb * G_BN + c * 32;
@@ -446,12 +469,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 const float *bias_t = s_bias + nb * G_BN;
                 float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f}, shift = 0.0f;
 #pragma unroll 1
-                for (int c = 0; c < G_BN / 32; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = valid ? fmaf(v[j], unscale, bias_t[c * 32 + j]) : 0.0f;
-                    if (c == 0) {
+                    if (c == c_lo) {
                         float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) { q0 += v[j]; q1 += v[j + 1]; q2 += v[j + 2]; q3 += v[j + 3]; }
@@ -472,17 +495,17 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     } else {
                         const int m_warp = mb * G_BM + wq * 32;
                         const size_t row0 = (a.G > 1 ? (size_t)g * a.rows_per_graph : 0) + m_warp;
-                        store_chunk_rows(s_out + wq * 32 * 33, v, lane, a.out_rows + row0 * a.N_total + nb * G_BN + c * 32, a.N_total,
+                        store_chunk_rows(s_tile, v, lane, a.out_rows + row0 * a.N_total + nb * G_BN + c * 32, a.N_total,
                                          min(32, (a.G > 1 ? a.rows_per_graph : a.M_total) - m_warp));
                     }
                 }
-                if (in_range) {
+                {
                     const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
-                    const float dm = s1 / (float)G_BN;
-                    float2 st;
-                    st.x = shift + dm;                          // mean of the tile's 256 values
-                    st.y = fmaxf(s2 - s1 * dm, 0.0f);           // sum of squared deviations from it
-                    *reinterpret_cast<float2 *>(a.stats + (((size_t)gg * a.rows_per_graph + i) * nb_per + nb) * 2) = st;
+                    const float dm = s1 / (float)(32 * kCPW);
+                    float2 st;                                  // mean of the tile's 256 values, sum of squared deviations from it
+                    combine_halves(as, shift + dm, fmaxf(s2 - s1 * dm, 0.0f), st.x, st.y);
+                    if (in_range && half == 0)
+                        *reinterpret_cast<float2 *>(a.stats + (((size_t)gg * a.rows_per_graph + i) * nb_per + nb) * 2) = st;
                 }
             } else {
                 // z = acc + bias; LayerNorm over the 256 columns this thread owns; ReLU   (gnn.py:31,45)
@@ -497,15 +520,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 // (shifted-data algorithm; ~2e-7 relative, the same as the two-pass form at this width)
                 float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f}, shift = 0.0f;   // 4 independent chains each
 #pragma unroll 1
-                for (int c = 0; c < G_BN / 32; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-                    if (c == 0) {          // shift = mean of the first 32 features (robust against a single outlier)
+                    if (c == c_lo) {       // shift = mean of this half's first 32 features (robust against a single outlier)
                         float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            q0 += fmaf(v[j], unscale, s_bias[j]); q1 += fmaf(v[j + 1], unscale, s_bias[j + 1]);
-                            q2 += fmaf(v[j + 2], unscale, s_bias[j + 2]); q3 += fmaf(v[j + 3], unscale, s_bias[j + 3]);
+                            q0 += fmaf(v[j], unscale, s_bias[c * 32 + j]); q1 += fmaf(v[j + 1], unscale, s_bias[c * 32 + j + 1]);
+                            q2 += fmaf(v[j + 2], unscale, s_bias[c * 32 + j + 2]); q3 += fmaf(v[j + 3], unscale, s_bias[c * 32 + j + 3]);
                         }
                         shift = ((q0 + q1) + (q2 + q3)) * (1.0f / 32.0f);
                     }
@@ -517,12 +540,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     }
                 }
                 const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
-                const float dm = s1 / (float)G_BN;
-                const float mean = shift + dm;
-                const float var = fmaxf(s2 - s1 * dm, 0.0f);        // = sum (z - mean)^2
+                const float dm = s1 / (float)(32 * kCPW);
+                float mean, var;                                     // of the whole 256-wide row: var = sum (z - mean)^2
+                combine_halves(as, shift + dm, fmaxf(s2 - s1 * dm, 0.0f), mean, var);
                 const float rstd = 1.0f / sqrtf(var / (float)G_BN + a.eps);
 #pragma unroll 1
-                for (int c = 0; c < G_BN / 32; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
@@ -537,7 +560,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         const int g0 = m_warp / a.rows_per_graph;
                         const int split = min(32, (g0 + 1) * a.rows_per_graph - m_warp);   // rows of the group's first graph
                         const float wrow = valid ? __ldg(a.pool_w + (size_t)gg * a.ld_w + i) : 0.0f;
-                        float *tile = s_out + wq * 32 * 33;
+                        float *tile = s_tile;
                         __syncwarp();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = v[j] * wrow;
@@ -566,7 +589,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         // rows of masked nodes are never read downstream (pooling stops at n_g): store all rows in range
                         const int m_warp = mb * G_BM + wq * 32;
                         const size_t row0 = (a.G > 1 ? (size_t)g * a.rows_per_graph : 0) + m_warp;
-                        store_chunk_rows(s_out + wq * 32 * 33, v, lane, a.out_rows + row0 * G_BN + c * 32, G_BN,
+                        store_chunk_rows(s_tile, v, lane, a.out_rows + row0 * G_BN + c * 32, G_BN,
                                          min(32, (a.G > 1 ? a.rows_per_graph : a.M_total) - m_warp));
                     } else {
                         // H^T[gg, n, i]: lanes hold consecutive nodes i -> coalesced 128-byte stores; nodes beyond n_g
@@ -596,17 +619,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (a.trace && threadIdx.x == 64) { a.trace[blockIdx.x * 8 + 5] = tr0; a.trace[blockIdx.x * 8 + 6] = tr1; }
     } else {
         // ===================== operand transform: fp32 landing tiles -> fp16 hi / lo tiles, in place =====================
-        // Thread t owns HALF of landing row (t & 127) of A and of B (+128): k-elements 16 h .. 16 h + 15 with h = t >> 7.  It
-        // reads its four 16-byte pieces per row (piece c of row r was stored by TMA at position c ^ (r & 7); a quarter-warp
-        // touches 8 rows = 8 distinct positions: no bank conflicts), waits until all 256 transform threads have read (the fp16
-        // tiles overwrite other threads' landing rows), then writes its 2 + 2 chunks per row (a quarter-warp writes one
-        // contiguous 128-byte core matrix).  Eight warps: two per scheduler, so one's shared-memory latency hides under the
-        // other's conversions (four warps measured 1030 cycles per k-block against 768 for the MMAs).
-        const int tid = (int)threadIdx.x - 6 * 32;                  // 0 .. 255
-        const int trow = tid & 127, th = tid >> 7;
+        // Thread t owns landing row (t & 127) of A and of B (+128) -- all of it with four transform warps, the half
+        // k = 16 h .. 16 h + 15 (h = t >> 7) with eight.  It reads its 16-byte pieces (piece c of row r was stored by TMA at
+        // position c ^ (r & 7); a quarter-warp touches 8 rows = 8 distinct positions: no bank conflicts), waits until all
+        // transform threads have read (the fp16 tiles overwrite other threads' landing rows), then writes 2 + 2 chunks per half
+        // row (a quarter-warp writes one contiguous 128-byte core matrix).  (Eight warps measured the same 1000 cycles per
+        // k-block as four -- shared-memory bandwidth, not issue slots, bounds the conversion -- so four of them went to the epilogue.)
+        constexpr int kXfThreads = 32 * G_XF_WARPS, kHP = 256 / kXfThreads;       // half rows per thread
+        const int tid = (int)threadIdx.x - G_XF_FIRST * 32;
+        const int trow = tid & 127, th0 = tid >> 7;
         const uint32_t ready_lead = mapa_u32(smem_u32(&ready[0]), 0);
         const uint32_t swz = (uint32_t)(trow & 7);
-        const uint32_t row_off = (uint32_t)((trow >> 3) * 512 + (trow & 7) * 16 + th * 256);   // of this half row inside an fp16 tile
+        const uint32_t row_off = (uint32_t)((trow >> 3) * 512 + (trow & 7) * 16);   // of this row inside an fp16 tile
         constexpr int kBPer = P::kBRows / 128;                      // B rows per thread
         int stage = 0;
         uint32_t phase = 0;
@@ -617,57 +641,68 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 { TR_T0(); mbar_wait(&full[stage], phase); TR_ADD(tr0); }     // this CTA's fp32 tiles have landed
                 const long long tr_w0 = a.trace ? clock64() : 0;
                 const uint32_t sb = smem_u32(smem + stage * P::kStage);
-                float4 va[4], vb[kBPer][4];
+                float4 va[kHP][4], vb[kBPer][kHP][4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) va[c] = lds128(sb + (uint32_t)trow * 128u + (((uint32_t)(4 * th + c) ^ swz) << 4));
-                if (!gather) {
+                for (int q = 0; q < kHP; ++q) {
+                    const int th = th0 + q * (kXfThreads / 128);
 #pragma unroll
-                    for (int h = 0; h < kBPer; ++h)
+                    for (int c = 0; c < 4; ++c) va[q][c] = lds128(sb + (uint32_t)trow * 128u + (((uint32_t)(4 * th + c) ^ swz) << 4));
+                    if (!gather) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            vb[h][c] = lds128(sb + kABytes + (uint32_t)(trow + 128 * h) * 128u + (((uint32_t)(4 * th + c) ^ swz) << 4));
-                } else {
-                    // gathered B: the landing tile is [k][f] (one bulk copy per node): read this thread's 16 nodes of feature row f
-                    // (32 lanes = 32 consecutive f: conflict-free)
+                        for (int h = 0; h < kBPer; ++h)
 #pragma unroll
-                    for (int h = 0; h < kBPer; ++h)
+                            for (int c = 0; c < 4; ++c)
+                                vb[h][q][c] = lds128(sb + kABytes + (uint32_t)(trow + 128 * h) * 128u + (((uint32_t)(4 * th + c) ^ swz) << 4));
+                    } else {
+                        // gathered B: the landing tile is [k][f] (one bulk copy per node): read this thread's nodes of feature row f
+                        // (32 lanes = 32 consecutive f: conflict-free)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const uint32_t base = sb + kABytes + (uint32_t)((16 * th + 4 * c) * (P::kBRows * 4) + (trow + 128 * h) * 4);
-                            vb[h][c].x = lds32(base);
-                            vb[h][c].y = lds32(base + P::kBRows * 4);
-                            vb[h][c].z = lds32(base + 2 * P::kBRows * 4);
-                            vb[h][c].w = lds32(base + 3 * P::kBRows * 4);
-                        }
+                        for (int h = 0; h < kBPer; ++h)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const uint32_t base = sb + kABytes + (uint32_t)((16 * th + 4 * c) * (P::kBRows * 4) + (trow + 128 * h) * 4);
+                                vb[h][q][c].x = lds32(base);
+                                vb[h][q][c].y = lds32(base + P::kBRows * 4);
+                                vb[h][q][c].z = lds32(base + 2 * P::kBRows * 4);
+                                vb[h][q][c].w = lds32(base + 3 * P::kBRows * 4);
+                            }
+                    }
                 }
-                asm volatile("bar.sync 2, %0;" ::"n"(32 * G_XF_WARPS) : "memory");       // every landing row is in registers
+                asm volatile("bar.sync 2, %0;" ::"n"(kXfThreads) : "memory");       // every landing row is in registers
                 if (a.bln_mr != nullptr) {
                     // B holds z^T of the previous layer: h = relu((z - mean_k) rstd_k gamma_f + beta_f) for feature row f, node k
                     const int kb = kidx < kA ? kidx : k2s + (kidx - kA);
-                    const int k0 = kb * G_BK + 16 * th;
                     const float2 *mr = reinterpret_cast<const float2 *>(a.bln_mr) + (size_t)(a.batched_b ? g : 0) * a.rows_per_graph;
 #pragma unroll
                     for (int h = 0; h < kBPer; ++h) {
                         const int f = nb * G_BN + rank * P::kBRows + trow + 128 * h;
                         const float gam = __ldg(a.bln_gamma + f), bet = __ldg(a.bln_beta + f);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            float *e = reinterpret_cast<float *>(&vb[h][c]);
+                        for (int q = 0; q < kHP; ++q) {
+                            const int k0 = kb * G_BK + 16 * (th0 + q * (kXfThreads / 128));
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int k = k0 + 4 * c + j;
-                                const float2 s2 = k < a.rows_per_graph ? __ldg(mr + k) : make_float2(0.0f, 0.0f);
-                                e[j] = fmaxf(fmaf(e[j] - s2.x, s2.y * gam, bet), 0.0f);
+                            for (int c = 0; c < 4; ++c) {
+                                float *e = reinterpret_cast<float *>(&vb[h][q][c]);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int k = k0 + 4 * c + j;
+                                    const float2 s2 = k < a.rows_per_graph ? __ldg(mr + k) : make_float2(0.0f, 0.0f);
+                                    e[j] = fmaxf(fmaf(e[j] - s2.x, s2.y * gam, bet), 0.0f);
+                                }
                             }
                         }
                     }
                 }
                 if (!(a.debug & 1)) {
-                    convert_half_row(va, scale_a, sb + row_off, sb + kABytes / 2 + row_off);
 #pragma unroll
-                    for (int h = 0; h < kBPer; ++h)
-                        convert_half_row(vb[h], scale_b, sb + kABytes + row_off + (uint32_t)(h * 16 * 512),
-                                         sb + kABytes + P::kBTile + row_off + (uint32_t)(h * 16 * 512));
+                    for (int q = 0; q < kHP; ++q) {
+                        const uint32_t ro = row_off + (uint32_t)((th0 + q * (kXfThreads / 128)) * 256);
+                        convert_half_row(va[q], scale_a, sb + ro, sb + kABytes / 2 + ro);
+#pragma unroll
+                        for (int h = 0; h < kBPer; ++h)
+                            convert_half_row(vb[h][q], scale_b, sb + kABytes + ro + (uint32_t)(h * 16 * 512),
+                                             sb + kABytes + P::kBTile + ro + (uint32_t)(h * 16 * 512));
+                    }
                 }
                 fence_proxy_async();                                // generic-proxy stores -> visible to the UMMA (async proxy)
                 __syncwarp();
