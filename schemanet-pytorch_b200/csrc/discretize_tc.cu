@@ -17,8 +17,8 @@
 //           sqrt(max(|x|^2 + |c|^2 - 2 x.c, 0)), lowest index on ties (the clamp and the sqrt create ties)
 //
 // Warp roles (320 threads, one CTA per SM, persistent over 128-row blocks):
-//   warp 0: TMA producer      warp 1: TMEM allocator + MMA issuer (one elected lane)      warps 2-9: epilogue (two per
-//   TMEM lane quarter, each scanning half of the accumulator's columns; merged through shared memory)
+//   warp 0: TMA producer      warp 1: TMEM allocator + MMA issuer (one elected lane)      warps 2-9: epilogue (kSplit = 2 per
+//   TMEM lane quarter, each scanning 1/kSplit of the accumulator's columns; merged through shared memory)
 // Pipelines: a 4-stage shared-memory ring (full/empty mbarriers, slots freed by tcgen05.commit) and a 2-stage TMEM
 // accumulator ring (tmem_full/tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda_fp16.h>
@@ -34,10 +34,12 @@ using namespace tc;
 constexpr int TC_BM = 128;       // token rows per tile (UMMA M)
 constexpr int TC_BK = 32;        // fp32 per k-block = one 128-byte swizzle row
 constexpr int TC_STAGES = 4;
-constexpr int TC_EPI_WARPS = 8;    // two warps per TMEM lane quarter: each takes half of a tile's column chunks
+constexpr int TC_EPI_WARPS = 8;    // kSplit warps per TMEM lane quarter: each takes 1/kSplit of a tile's column chunks (16 warps
+                                   // measured r02: cfg2 50.0 vs 50.4 us, ImageNet shape 1034 vs 1004 us -- the epilogue is not latency-bound)
+constexpr int kSplit = TC_EPI_WARPS / 4;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int kOverflowMark = -1;
-constexpr int kListSlots = 14;                // per-half shared-memory list capacity (4 stages + 2 lists fit in 227 KB)
+constexpr int kListSlots = kSplit == 2 ? 14 : 6;   // per-split shared-memory list capacity (4 stages + the lists fit in 227 KB)
 constexpr int kCandStride = kListSlots + 1;   // slot kListSlots absorbs the stores of a full list
 
 struct DiscTcArgs {
@@ -63,9 +65,9 @@ struct DiscTcSmem {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = TC_STAGES * kStageBytes;
     static constexpr int kCandOffset = kBarOffset + 256;
-    // two candidate lists per row (one per column half) + the halves' running minima / counts
-    static constexpr int kHalfOffset = kCandOffset + 2 * TC_BM * kCandStride * 8;
-    static constexpr int kTotal = kHalfOffset + 2 * TC_BM * 8 + 1024;   // + slack for 1024-B alignment
+    // kSplit candidate lists per row (one per column group) + the groups' running minima / counts
+    static constexpr int kHalfOffset = kCandOffset + kSplit * TC_BM * kCandStride * 8;
+    static constexpr int kTotal = kHalfOffset + kSplit * TC_BM * 8 + 1024;   // + slack for 1024-B alignment
 };
 
 // kHalf: operands are fp16 copies (64 elements per 128-byte swizzle row, kind::f16, UMMA K = 16) instead of the fp32
@@ -96,9 +98,9 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 2);
     float *cand_s = (float *)(smem + S::kCandOffset);
-    int *cand_i = (int *)(cand_s + 2 * TC_BM * kCandStride);
+    int *cand_i = (int *)(cand_s + kSplit * TC_BM * kCandStride);
     float *half_m = (float *)(smem + S::kHalfOffset);
-    int *half_c = (int *)(half_m + 2 * TC_BM);
+    int *half_c = (int *)(half_m + kSplit * TC_BM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;      // 0 = the CTA that issues the MMAs
@@ -188,14 +190,15 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
         // ===================== epilogue: fused score + running argmin + near-tie candidates =====================
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;              // which half of every tile's column chunks this warp scans
+        const int half = (warp - 2) >> 2;              // which group of every tile's column chunks this warp scans (0 .. kSplit-1)
         const int row_in_tile = wq * 32 + lane;
         float *my_s = cand_s + (half * TC_BM + row_in_tile) * kCandStride;
         int *my_i = cand_i + (half * TC_BM + row_in_tile) * kCandStride;
         const uint32_t my_base = smem_u32(my_s), my_end = my_base + 4u * kListSlots;
-        constexpr uint32_t kIdxDelta = 2u * TC_BM * kCandStride * 4u;   // byte distance cand_s -> cand_i
+        constexpr uint32_t kIdxDelta = (uint32_t)kSplit * TC_BM * kCandStride * 4u;   // byte distance cand_s -> cand_i
         (void)my_i;
-        constexpr int kChunksPerHalf = (BN / 32) / 2;
+        constexpr int kChunks = BN / 32;
+        constexpr int kChunksPerHalf = kChunks >= kSplit ? kChunks / kSplit : 1;   // (narrow tiles leave the last groups idle)
         // (tf32 operands: the residuals are those of truncation to 10 mantissa bits, an upper bound element by element of what
         // the hardware drops whether it truncates or rounds)
         const float cmax2 = __uint_as_float(a.cmax_bits[0]), dcmax2 = __uint_as_float(a.cmax_bits[1]);
@@ -223,7 +226,7 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-                for (int c = half * kChunksPerHalf; c < (half + 1) * kChunksPerHalf; ++c) {
+                for (int c = half * kChunksPerHalf; c < min((half + 1) * kChunksPerHalf, kChunks); ++c) {
                     const int n_base = nb * BN + c * 32;
                     if (n_base >= a.M || (a.debug & 1)) break;
                     float v[32];
@@ -276,12 +279,14 @@ discretize_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             half_c[half * TC_BM + row_in_tile] = cnt;
             asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
             if (half == 0 && valid) {
-                const float m_all = fminf(m_run, half_m[TC_BM + row_in_tile]);
+                float m_all = m_run;
+#pragma unroll
+                for (int h = 1; h < kSplit; ++h) m_all = fminf(m_all, half_m[h * TC_BM + row_in_tile]);
                 const float thr = m_all + band;
                 bool overflow = false;
                 int keep = 0, first = 0;
 #pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < kSplit; ++h) {
                     const int cnt_h = half_c[h * TC_BM + row_in_tile];
                     const float *ls = cand_s + (h * TC_BM + row_in_tile) * kCandStride;
                     const int *li = cand_i + (h * TC_BM + row_in_tile) * kCandStride;
@@ -373,16 +378,28 @@ rows_to_half_kernel(const float *__restrict__ x, int64_t rows, int d, unsigned s
         const float2 *p = reinterpret_cast<const float2 *>(x + r * d);
         unsigned *q = reinterpret_cast<unsigned *>(xh + r * d);
         float s = 0.0f, e = 0.0f;
-        for (int k = lane; k < d / 2; k += kWarp) {
-            const float2 v = p[k];
-            s = fmaf(v.x, v.x, s);
-            s = fmaf(v.y, v.y, s);
-            const __half h0 = __float2half_rn(fminf(fmaxf(v.x, -65504.0f), 65504.0f));
-            const __half h1 = __float2half_rn(fminf(fmaxf(v.y, -65504.0f), 65504.0f));
-            const float d0 = v.x - __half2float(h0), d1 = v.y - __half2float(h1);    // exact in fp32 (NaN / inf stay NaN / inf)
-            e = fmaf(d0, d0, e);
-            e = fmaf(d1, d1, e);
-            q[k] = (unsigned)__half_as_ushort(h0) | ((unsigned)__half_as_ushort(h1) << 16);
+        // batches of 8 independent 8-byte loads per lane (a whole d = 512 row in flight per warp); the running sums keep
+        // the element order of the plain loop, so the norms do not depend on the batching
+        for (int k0 = lane; k0 < d / 2; k0 += 8 * kWarp) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u * kWarp;
+                v[u] = (k < d / 2) ? __ldcs(p + k) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u * kWarp;
+                if (k >= d / 2) break;
+                s = fmaf(v[u].x, v[u].x, s);
+                s = fmaf(v[u].y, v[u].y, s);
+                const __half h0 = __float2half_rn(fminf(fmaxf(v[u].x, -65504.0f), 65504.0f));
+                const __half h1 = __float2half_rn(fminf(fmaxf(v[u].y, -65504.0f), 65504.0f));
+                const float d0 = v[u].x - __half2float(h0), d1 = v[u].y - __half2float(h1);    // exact in fp32 (NaN / inf stay NaN / inf)
+                e = fmaf(d0, d0, e);
+                e = fmaf(d1, d1, e);
+                q[k] = (unsigned)__half_as_ushort(h0) | ((unsigned)__half_as_ushort(h1) << 16);
+            }
         }
         s = warp_sum(s);
         e = warp_sum(e) * 1.0000005f;          // the sum itself is rounded: keep the residual norm an upper bound
