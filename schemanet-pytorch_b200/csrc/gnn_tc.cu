@@ -46,14 +46,13 @@ constexpr int G_BM = 128;
 constexpr int G_BN = 256;      // == embed_dim
 constexpr int G_BK = 32;
 constexpr int kGatherMaxNodes = 1024;                      // node codes of one graph held in shared memory by a gathering GEMM
-// Warp budget (448 threads, 128 registers each).  Measured on B200 (profiles/r02_experiments.md): 4 epilogue + 8 transform warps
-// and 8 + 4 give the same cfg2 step (0.675 / 0.679 ms) -- the second epilogue warpgroup shortens the exposed last epilogue, the
-// 4-warp conversion (64 live floats per thread, spills) gives it back -- and 8 + 4 is 4 % slower at cfg4, where the transform
-// also applies LayerNorm.  G_EPI_WARPS = 8: two warps per TMEM lane quarter, each owns half of a tile's columns.
-constexpr int G_EPI_WARPS = 4;
+// Warp budget: producer + MMA issuer + EW epilogue warps + 8 operand-transform warps; EW is a template parameter of the kernel.
+// EW = 8 (two warps per TMEM lane quarter, each owns half of a tile's columns; 576 threads, 96 registers, one stage less): the
+// embed_dim = 256 launches, whose 6-8 k-block tiles are bound by the LayerNorm epilogue.  EW = 4 (448 threads, 128 registers):
+// everything else -- at cfg4 the transform also applies LayerNorm and the register cap of the larger block costs more than the
+// second epilogue warpgroup saves.  Same-box A/B on B200 (profiles/r02_experiments.md): cfg2 0.685 -> 0.665 ms, cfg3 1.019 ->
+// 0.996 ms with EW = 8; cfg4 14.78 -> 15.05 ms, hence 4 there.  (8 epilogue + 4 transform warps: no gain at cfg2, -4 % at cfg4.)
 constexpr int G_XF_WARPS = 8;                              // operand-transform warps
-constexpr int G_XF_FIRST = 2 + G_EPI_WARPS;                // first transform warp
-constexpr int G_THREADS = 32 * (G_XF_FIRST + G_XF_WARPS);
 constexpr int kABytes = G_BM * G_BK * 4;                 // 16 KB
 
 enum { EPI_STORE_ROWS = 0, EPI_LN_RELU_T = 1, EPI_LN_RELU_ROWS = 2, EPI_BIAS_ROWS = 3,
@@ -209,26 +208,29 @@ __device__ __forceinline__ void convert_half_row(const float4 (&v)[4], float s, 
 
 // Shared-memory plan.  A stage is the fp32 landing area of one k-block: 128 A rows (16 KB) + this CTA's B rows (CTA pair:
 // 128 rows, 16 KB; single CTA: 256 rows, 32 KB).  The conversion is in place: each region ends up as [hi tile | lo tile].
-template <int CTAS>
+template <int CTAS, int EW>
 struct GemmPlan {
     static constexpr int kBRows = G_BN / CTAS;
     static constexpr int kBBytesL = kBRows * G_BK * 4;            // landing bytes of the B rows = hi tile + lo tile
     static constexpr int kBTile = kBBytesL / 2;
     static constexpr int kStage = kABytes + kBBytesL;
-    static constexpr int kStages = G_EPI_WARPS == 4 ? (CTAS == 1 ? 4 : 6) : (CTAS == 1 ? 3 : 5);
+    static constexpr int kStages = EW == 4 ? (CTAS == 1 ? 4 : 6) : (CTAS == 1 ? 3 : 5);
     static constexpr int kBar = kStages * kStage;
     static constexpr int kParam = kBar + 256;
     static constexpr int kStageOut = kParam + (2 * G_BN + kMaxDim) * 4;   // gamma, beta (LN: 256 wide) + bias (up to kMaxDim)
-    static constexpr int kXch = kStageOut + G_EPI_WARPS * 32 * 33 * 4;      // LayerNorm partials exchanged by the two column halves
+    static constexpr int kXch = kStageOut + EW * 32 * 33 * 4;      // LayerNorm partials exchanged by the two column halves
     static constexpr int kIds = kXch + 2 * 2 * G_BM * 8;                    // node codes of the current graph (gathered B operand)
     static constexpr int kTotal = kIds + 1024 * 4 + 1024;            // (kGatherMaxNodes int32)
 };
 
-template <int EPI, int CTAS>
-__global__ void __launch_bounds__(G_THREADS, 1)
+template <int EPI, int CTAS, int EW>
+__global__ void __launch_bounds__(32 * (2 + EW + G_XF_WARPS), 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs a)
 {
-    using P = GemmPlan<CTAS>;
+    constexpr int G_EPI_WARPS = EW;
+    constexpr int G_XF_FIRST = 2 + G_EPI_WARPS;                // first transform warp
+    constexpr int G_THREADS = 32 * (G_XF_FIRST + G_XF_WARPS);
+    using P = GemmPlan<CTAS, EW>;
     constexpr int S = P::kStages;
     const long long tr_entry = a.trace ? clock64() : 0;
     unsigned long long tr_gt0 = 0;
@@ -1493,13 +1495,13 @@ static int gemm_ctas()
     return v;
 }
 
-template <int EPI, int CTAS>
+template <int EPI, int CTAS, int EW>
 static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const char *name, cudaStream_t st)
 {
-    using P = GemmPlan<CTAS>;
+    using P = GemmPlan<CTAS, EW>;
     static bool configured = false;
     if (!configured) {
-        SH_CHECK_CUDA(cudaFuncSetAttribute(gemm3x_kernel<EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kTotal));
+        SH_CHECK_CUDA(cudaFuncSetAttribute(gemm3x_kernel<EPI, CTAS, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kTotal));
         configured = true;
     }
     const int units = a.G * ceil_div(a.M_total, G_BM * CTAS) * (a.N_total / G_BN);
@@ -1517,7 +1519,7 @@ static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const c
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(num_units * CTAS);
-    cfg.blockDim = dim3(G_THREADS);
+    cfg.blockDim = dim3(32 * (2 + EW + G_XF_WARPS));
     cfg.dynamicSmemBytes = P::kTotal;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1528,7 +1530,7 @@ static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const c
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     prof_begin(name, st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm3x_kernel<EPI, CTAS>, maps[0], maps[1], a2);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm3x_kernel<EPI, CTAS, EW>, maps[0], maps[1], a2);
     prof_end(st);
     if (e != cudaSuccess) { set_error("%s launch -> %s", name, cudaGetErrorString(e)); return 1; }
     SH_CHECK_LAUNCH();
@@ -1563,11 +1565,11 @@ static int launch_gemm3x_n(const CUtensorMap *maps, const GemmTcArgs &a, const c
 }
 
 // maps: {A, B} for one CTA per row block, maps2: the same with 128-row B boxes for CTA pairs
-template <int EPI>
+template <int EPI, int EW = 4>
 static int launch_gemm3x(const CUtensorMap *maps, const CUtensorMap *maps2, const GemmTcArgs &a, const char *name, cudaStream_t st)
 {
-    if (gemm_ctas() == 2) return launch_gemm3x_n<EPI, 2>(maps2, a, name, st);
-    return launch_gemm3x_n<EPI, 1>(maps, a, name, st);
+    if (gemm_ctas() == 2) return launch_gemm3x_n<EPI, 2, EW>(maps2, a, name, st);
+    return launch_gemm3x_n<EPI, 1, EW>(maps, a, name, st);
 }
 
 // 3-D map over [batch, rows, cols]; a batch of 1 still uses rank 3 so that the kernel issues one kind of TMA
@@ -1863,14 +1865,14 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
             a.row_sizes = row_sizes;
             a.bias = p->lin_b[0]; a.gamma = p->ln_w[0]; a.beta = p->ln_b[0]; a.eps = p->ln_eps;
             a.out_t = xout; a.ldk = ldk; a.out_rows = b.h_rows; a.amax_out = b.amax + AM_X + l + 1;
-            if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
-            else { if (launch_gemm3x<EPI_LN_RELU_T>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
+            if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS, 8>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
+            else { if (launch_gemm3x<EPI_LN_RELU_T, 8>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }
             float *t = xin; xin = xout; xout = t;
             continue;
         }
         // Y = Adj X
         a.out_rows = b.y; a.amax_out = b.amax + AM_Y + l;
-        if (launch_gemm3x<EPI_STORE_ROWS>(m1, m1p, a, "gnn_adj_gemm_tc", st)) return 1;
+        if (launch_gemm3x<EPI_STORE_ROWS, 8>(m1, m1p, a, "gnn_adj_gemm_tc", st)) return 1;
         // H = relu(LN(Y W^T + b)); the weight matrix is read where it lies (split in shared memory like every operand)
         SH_REQUIRE(((uintptr_t)p->lin_w[l] & 15) == 0, "gnn: Linear weights must be 16-byte aligned for TMA");
         CUtensorMap wm, wm2;
@@ -1889,9 +1891,9 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
                 // weighted pooling fused into the epilogue: H of the last layer is never written
                 c.pool_w = vertex_w; c.ld_w = ld_v; c.pool_groups = b.pool_groups;
                 pooled_in_epilogue = true;
-                if (launch_gemm3x<EPI_LN_RELU_ROWS>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1;
+                if (launch_gemm3x<EPI_LN_RELU_ROWS, 8>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1;
             }
-            else { if (launch_gemm3x<EPI_LN_RELU_T>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
+            else { if (launch_gemm3x<EPI_LN_RELU_T, 8>(m2, m2p, c, "gnn_linear_ln_tc", st)) return 1; }
         } else {
             // wide embeddings: bias in the GEMM epilogue, LayerNorm + ReLU (+ transpose) as a separate pass
             if (launch_gemm3x<EPI_BIAS_ROWS>(m2, m2p, c, "gnn_linear_tc", st)) return 1;
