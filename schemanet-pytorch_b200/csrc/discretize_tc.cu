@@ -360,7 +360,14 @@ codebook_norms_kernel(const float *__restrict__ C, int M, int padded, int d, flo
         if (r >= M) { if (lane == 0) cn[r] = INFINITY; continue; }
         const float *p = C + (size_t)r * d;
         float s = 0.0f;
-        for (int k = lane; k < d; k += kWarp) s = fmaf(p[k], p[k], s);
+        for (int k0 = lane; k0 < d; k0 += 8 * kWarp) {      // 8 loads in flight per lane, folded in the order of the plain loop
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (k0 + u * kWarp < d) ? p[k0 + u * kWarp] : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (k0 + u * kWarp < d) s = fmaf(v[u], v[u], s);
+        }
         s = warp_sum(s);
         if (lane == 0) { cn[r] = s; atomicMax(cmax_bits, __float_as_uint(s)); }
     }

@@ -871,21 +871,32 @@ embed_gather_t_kernel(const float *__restrict__ emb, const int64_t *__restrict__
     if (i0 >= max(32, (n_g + 31) / 32 * 32)) return;   // past the k-blocks the adjacency GEMM reads for this graph
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int dn = min(256, D - d0);                    // features of this slab (multiple of 32)
-    for (int r = warp; r < 32; r += 8) {               // node i0 + r
-        const int i = i0 + r;
-        const float *row = (i < n_g) ? emb + (size_t)ids[(size_t)g * ld_ids + i] * D + d0 : nullptr;
+    // all 32 loads of a warp (4 nodes x 8 row segments) are issued before the first one is used: written as a plain
+    // load-then-store loop the compiler kept one load in flight per warp and the kernel ran at L2 latency (28 us at cfg2)
+    const float *rows[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                     // node i0 + warp + 8 q
+        const int i = i0 + warp + 8 * q;
+        rows[q] = (i < n_g) ? emb + (size_t)ids[(size_t)g * ld_ids + i] * D + d0 : nullptr;
+    }
+    float v[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[q][c] = (rows[q] != nullptr && c * 32 < dn) ? __ldg(rows[q] + c * 32 + lane) : 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-            if (c * 32 < dn) tile[r][c * 32 + lane] = row ? __ldg(row + c * 32 + lane) : 0.0f;
-    }
+            if (c * 32 < dn) tile[warp + 8 * q][c * 32 + lane] = v[q][c];
     __syncthreads();
     const int i = i0 + lane;
     float mx = 0.0f;
     if (i < ldk)
         for (int d = warp; d < dn; d += 8) {           // feature d0 + d, nodes i0 .. i0 + 31 (coalesced along i)
-            const float v = tile[lane][d];
-            xt[((size_t)g * D + d0 + d) * ldk + i] = v;
-            mx = fmaxf(mx, fabsf(v));
+            const float t = tile[lane][d];
+            xt[((size_t)g * D + d0 + d) * ldk + i] = t;
+            mx = fmaxf(mx, fabsf(t));
         }
     record_amax(amax, mx);
 }
@@ -951,15 +962,31 @@ pool_groups_fc_kernel(const float *__restrict__ groups, const int32_t *__restric
     const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_g = sizes ? sizes[g] : n_fixed;
     const float div = (float)(mean_div ? *mean_div : n_fixed);
+    // (every loop below issues its batch of independent loads before the first use: these kernels are a few dependent L2
+    // round trips long, and a load-use-load-use chain made them 19 us at cfg2)
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float acc = 0.0f;
         if (n_g > 0) {
             const int r0 = g * n_fixed, q0 = r0 / 32, q1 = (r0 + n_g - 1) / 32;
-            for (int q = q0; q <= q1; ++q) acc += groups[((size_t)q * 2 + (((q * 32) / n_fixed == g) ? 0 : 1)) * D + d];
+            for (int qb = q0; qb <= q1; qb += 8) {
+                float t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int q = qb + u;
+                    t[u] = q <= q1 ? groups[((size_t)q * 2 + (((q * 32) / n_fixed == g) ? 0 : 1)) * D + d] : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (qb + u <= q1) acc += t[u];
+            }
         }
         if (extra) {
+            float t[kTableSlices];
+#pragma unroll
+            for (int y = 0; y < kTableSlices; ++y) t[y] = extra[((size_t)g * kTableSlices + y) * D + d];
             float e = 0.0f;
-            for (int y = 0; y < kTableSlices; ++y) e += extra[((size_t)g * kTableSlices + y) * D + d];
+#pragma unroll
+            for (int y = 0; y < kTableSlices; ++y) e += t[y];
             acc += e;
         }
         pooled[d] = acc / div;
@@ -967,12 +994,35 @@ pool_groups_fc_kernel(const float *__restrict__ groups, const int32_t *__restric
     __syncthreads();
     const int per = (D + gridDim.y - 1) / gridDim.y;
     const int o_end = min(D, (int)(blockIdx.y + 1) * per);
-    for (int o = blockIdx.y * per + warp; o < o_end; o += (int)(blockDim.x >> 5)) {
-        const float *w = fc_w + (size_t)o * D;
-        float acc = 0.0f;
-        for (int d = lane; d < D; d += kWarp) acc = fmaf(pooled[d], w[d], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) out[(size_t)g * D + o] = acc + fc_b[o];
+    const int nwarps = (int)(blockDim.x >> 5);
+    // a warp computes four outputs at a time; per output the products are folded in ascending d per lane, then across lanes
+    for (int o0 = blockIdx.y * per + warp; o0 < o_end; o0 += 4 * nwarps) {
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int d0 = lane; d0 < D; d0 += 8 * kWarp) {
+            float wv[4][8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = o0 + j * nwarps;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int d = d0 + u * kWarp;
+                    wv[j][u] = (o < o_end && d < D) ? __ldg(fc_w + (size_t)o * D + d) : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int d = d0 + u * kWarp;
+                    if (d < D) acc[j] = fmaf(pooled[d], wv[j][u], acc[j]);
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + j * nwarps;
+            const float r = warp_sum(acc[j]);
+            if (lane == 0 && o < o_end) out[(size_t)g * D + o] = r + fc_b[o];
+        }
     }
 }
 
@@ -996,8 +1046,20 @@ pool_table_rows_kernel(const float *__restrict__ T, const int64_t *__restrict__ 
     const int64_t *idk = ids + (size_t)k * Vc;
     const float *wk = w + (size_t)k * Vc;
     float acc = 0.0f;
-#pragma unroll 8
-    for (int i = n_act[k] + blockIdx.y; i < Vc; i += kTableSlices) acc = fmaf(__ldg(T + (size_t)idk[i] * D + d), wk[i], acc);
+    int i = n_act[k] + blockIdx.y;
+    // eight gathered rows in flight per thread (ids, then table entries), folded in the order of the plain loop
+    for (; i + 7 * kTableSlices < Vc; i += 8 * kTableSlices) {
+        float t[8], ww[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int ii = i + u * kTableSlices;
+            t[u] = __ldg(T + (size_t)idk[ii] * D + d);
+            ww[u] = wk[ii];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(t[u], ww[u], acc);
+    }
+    for (; i < Vc; i += kTableSlices) acc = fmaf(__ldg(T + (size_t)idk[i] * D + d), wk[i], acc);
     extra[((size_t)k * kTableSlices + blockIdx.y) * D + d] = acc;
 }
 
