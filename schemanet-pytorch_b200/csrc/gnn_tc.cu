@@ -866,19 +866,24 @@ embed_gather_t_kernel(const float *__restrict__ emb, const int64_t *__restrict__
 {
     __shared__ float tile[32][257];
     const int g = blockIdx.z;
-    const int n_g = sizes ? sizes[g] : n_fixed;
     const int i0 = blockIdx.x * 32, d0 = blockIdx.y * 256;
-    if (i0 >= max(32, (n_g + 31) / 32 * 32)) return;   // past the k-blocks the adjacency GEMM reads for this graph
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_g = sizes ? sizes[g] : n_fixed;
+    // the codes of this warp's four nodes are requested together with the graph's size (every slot < n_fixed is readable), so
+    // the kernel is three dependent round trips long -- size + codes, table rows, stores -- instead of four
+    int64_t code[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                     // node i0 + warp + 8 q
+        const int i = i0 + warp + 8 * q;
+        code[q] = (i < n_fixed) ? ids[(size_t)g * ld_ids + i] : 0;
+    }
+    if (i0 >= max(32, (n_g + 31) / 32 * 32)) return;   // past the k-blocks the adjacency GEMM reads for this graph
     const int dn = min(256, D - d0);                    // features of this slab (multiple of 32)
     // all 32 loads of a warp (4 nodes x 8 row segments) are issued before the first one is used: written as a plain
     // load-then-store loop the compiler kept one load in flight per warp and the kernel ran at L2 latency (28 us at cfg2)
     const float *rows[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {                     // node i0 + warp + 8 q
-        const int i = i0 + warp + 8 * q;
-        rows[q] = (i < n_g) ? emb + (size_t)ids[(size_t)g * ld_ids + i] * D + d0 : nullptr;
-    }
+    for (int q = 0; q < 4; ++q) rows[q] = (i0 + warp + 8 * q < n_g) ? emb + (size_t)code[q] * D + d0 : nullptr;
     float v[4][8];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -973,7 +978,9 @@ pool_groups_fc_kernel(const float *__restrict__ groups, const int32_t *__restric
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int q = qb + u;
-                    t[u] = q <= q1 ? groups[((size_t)q * 2 + (((q * 32) / n_fixed == g) ? 0 : 1)) * D + d] : 0.0f;
+                    // slot 0: g is the first graph of the 32-row group, i.e. the group starts inside g (no division: q * 32 <= r0 +
+                    // n_g - 1 < r0 + n_fixed already holds for q <= q1)
+                    t[u] = q <= q1 ? groups[((size_t)q * 2 + ((q * 32 >= r0) ? 0 : 1)) * D + d] : 0.0f;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
@@ -1041,25 +1048,32 @@ __global__ void __launch_bounds__(256)
 pool_table_rows_kernel(const float *__restrict__ T, const int64_t *__restrict__ ids, const float *__restrict__ w,
                        const int32_t *__restrict__ n_act, int Vc, int D, float *__restrict__ extra)
 {
+    // the slice's codes and weights go to shared memory in one round trip (they are the same for every thread), then 16 table
+    // entries per thread are in flight at a time; the sum is folded in the order of the plain loop over i
+    extern __shared__ unsigned char pool_smem[];
+    int *s_code = reinterpret_cast<int *>(pool_smem);
+    float *s_w = reinterpret_cast<float *>(s_code + (Vc + kTableSlices - 1) / kTableSlices);
     const int k = blockIdx.x, d = threadIdx.x;
-    if (d >= D) return;
     const int64_t *idk = ids + (size_t)k * Vc;
     const float *wk = w + (size_t)k * Vc;
-    float acc = 0.0f;
-    int i = n_act[k] + blockIdx.y;
-    // eight gathered rows in flight per thread (ids, then table entries), folded in the order of the plain loop
-    for (; i + 7 * kTableSlices < Vc; i += 8 * kTableSlices) {
-        float t[8], ww[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int ii = i + u * kTableSlices;
-            t[u] = __ldg(T + (size_t)idk[ii] * D + d);
-            ww[u] = wk[ii];
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc = fmaf(t[u], ww[u], acc);
+    const int first = n_act[k] + blockIdx.y;
+    const int cnt = first < Vc ? (Vc - first + kTableSlices - 1) / kTableSlices : 0;
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+        s_code[j] = (int)idk[first + j * kTableSlices];
+        s_w[j] = wk[first + j * kTableSlices];
     }
-    for (; i < Vc; i += kTableSlices) acc = fmaf(__ldg(T + (size_t)idk[i] * D + d), wk[i], acc);
+    __syncthreads();
+    if (d >= D) return;
+    float acc = 0.0f;
+    int j = 0;
+    for (; j + 16 <= cnt; j += 16) {
+        float t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = __ldg(T + (size_t)s_code[j + u] * D + d);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc = fmaf(t[u], s_w[j + u], acc);
+    }
+    for (; j < cnt; ++j) acc = fmaf(__ldg(T + (size_t)s_code[j] * D + d), s_w[j], acc);
     extra[((size_t)k * kTableSlices + blockIdx.y) * D + d] = acc;
 }
 
@@ -1755,7 +1769,7 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
                 return 1;
             float *t = cur; cur = nxt; nxt = t;
         }
-        SH_LAUNCH("gnn_pool_table_rows", ts, pool_table_rows_kernel<<<dim3(G, kTableSlices), 256, 0, ts>>>(cur, ids, vertex_w, row_sizes, n_fixed, D, b.pool_extra));
+        SH_LAUNCH("gnn_pool_table_rows", ts, pool_table_rows_kernel<<<dim3(G, kTableSlices), 256, (size_t)ceil_div(n_fixed, kTableSlices) * 8, ts>>>(cur, ids, vertex_w, row_sizes, n_fixed, D, b.pool_extra));
         SH_CHECK_LAUNCH();
     }
     {

@@ -3,7 +3,7 @@
 D=schemanet-pytorch_b200/schemanet_b200
 mkdir -p gpurun_out
 for rep in 1 2 3; do
-for v in a b; do
+for v in ${AB_VARIANTS:-a b}; do
   cp $D/variant_$v.so $D/libschemahead.so
   timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/ab_$v.json 2>/dev/null
   python - $v $rep <<'PY'
@@ -14,7 +14,7 @@ print(sys.argv[1], "cfg2 step %.4f ms" % d["ms_per_step"], sel)
 PY
 done
 done
-for v in a b; do
+for v in ${AB_VARIANTS:-a b}; do
   cp $D/variant_$v.so $D/libschemahead.so
   for c in ${AB_CONFIGS:-cfg3 cfg4}; do
   timeout 500 python bench.py --config $c --steps 8 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/ab_${c}_$v.json 2>/dev/null
@@ -25,5 +25,5 @@ print(sys.argv[1], sys.argv[2], "step %.4f ms" % d["ms_per_step"])
 PY
   done
 done
-cp $D/variant_b.so $D/libschemahead.so
+cp $D/variant_${AB_FINAL:-b}.so $D/libschemahead.so
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "gnn or class or cfg or golden or head" 2>&1 | tail -2
