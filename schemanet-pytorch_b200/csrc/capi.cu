@@ -170,7 +170,7 @@ extern "C" int sh_dev_discretize(const float *tokens, const float *vocab, int64_
         tensor = half || discretize_tc_supported(R, d, M, false);
     }
     SH_CHECK_CUDA(cudaMemsetAsync(ws.counters, 0, 256, st));
-    if (launch_codebook_norms(vocab, M, d, ws, st)) return 1;
+    if (launch_codebook_norms(vocab, M, d, ws, st, tensor && half)) return 1;     // (+ the fp16 codebook copy of the f16 coarse pass)
     if (tensor) {
         if (launch_discretize_tc(tokens, vocab, R, d, M, out_idx, idx_rows, idx_row_stride, idx_col_stride, ws, half, st)) return 1;
     } else {

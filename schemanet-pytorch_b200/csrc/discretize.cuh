@@ -49,7 +49,7 @@ inline DiscWorkspace carve_disc_workspace(void *base, int64_t R, int M, int d)
 int launch_row_sqnorm(const float *x, int64_t rows, int d, float *out, cudaStream_t st, float *resid = nullptr,
                       unsigned *max_resid_bits = nullptr);
 // |c_j|^2 into ws.cn (+inf padding up to a multiple of 256) and max_j |c_j|^2 into ws.counters[2]
-int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws, cudaStream_t st);
+int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws, cudaStream_t st, bool half_copy = false);
 int launch_gather(const float *vocab, const int64_t *idx, int64_t idx_rows, int64_t idx_row_stride,
                   int64_t idx_col_stride, int64_t R, int d, float *out, cudaStream_t st);
 int launch_discretize_exact(const float *X, const float *C, const float *cn, int64_t R, int d, int M, int64_t *out_idx,

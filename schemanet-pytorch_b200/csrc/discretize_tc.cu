@@ -351,9 +351,14 @@ discretize_recheck_kernel(const float *__restrict__ X, const float *__restrict__
     }
 }
 
-// |c_j|^2 (+inf padding up to `padded`) and the bit pattern of max_j |c_j|^2
+__device__ __forceinline__ void warp_row_to_half(const float *__restrict__ row, int d, unsigned short *__restrict__ out, float &norm,
+                                                 float &resid);
+
+// |c_j|^2 (+inf padding up to `padded`) and the bit pattern of max_j |c_j|^2; with `ch` also the fp16 copy of the codebook and
+// the running maximum of its rounding residuals (what rows_to_half_kernel would produce: one launch less on the stage's chain)
 __global__ void __launch_bounds__(256)
-codebook_norms_kernel(const float *__restrict__ C, int M, int padded, int d, float *__restrict__ cn, unsigned *cmax_bits)
+codebook_norms_kernel(const float *__restrict__ C, int M, int padded, int d, float *__restrict__ cn, unsigned *cmax_bits,
+                      unsigned short *__restrict__ ch, unsigned *max_resid_bits)
 {
     const int lane = threadIdx.x & 31;
     for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < padded; r += gridDim.x * 8) {
@@ -370,46 +375,61 @@ codebook_norms_kernel(const float *__restrict__ C, int M, int padded, int d, flo
         }
         s = warp_sum(s);
         if (lane == 0) { cn[r] = s; atomicMax(cmax_bits, __float_as_uint(s)); }
+        if (ch != nullptr) {
+            float s2, e;
+            warp_row_to_half(p, d, ch + (size_t)r * d, s2, e);            // (the row is in L1 by now)
+            if (lane == 0) atomicMax(max_resid_bits, __float_as_uint(fabsf(e)));
+        }
     }
 }
 
-// fp32 rows -> fp16 copy (round to nearest even, saturated to the fp16 range), |row|^2 of the ORIGINAL fp32 row and the
-// squared norm of the rounding residual |row - fp16(row)|^2 (the measured quantity the candidate band is built from);
-// max_resid_bits (codebook): running maximum of the residuals' bit patterns.  One warp per row.
+// One warp converts one fp32 row to fp16 (round to nearest even, saturated to the fp16 range) and returns, on every lane,
+// |row|^2 of the ORIGINAL fp32 row and an upper bound of the squared norm of the rounding residual |row - fp16(row)|^2 (the
+// measured quantity the candidate band is built from).
+__device__ __forceinline__ void warp_row_to_half(const float *__restrict__ row, int d, unsigned short *__restrict__ out, float &norm,
+                                                 float &resid)
+{
+    const int lane = threadIdx.x & 31;
+    const float2 *p = reinterpret_cast<const float2 *>(row);
+    unsigned *q = reinterpret_cast<unsigned *>(out);
+    float s = 0.0f, e = 0.0f;
+    // batches of 8 independent 8-byte loads per lane (a whole d = 512 row in flight per warp); the running sums keep
+    // the element order of the plain loop, so the norms do not depend on the batching
+    for (int k0 = lane; k0 < d / 2; k0 += 8 * kWarp) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * kWarp;
+            v[u] = (k < d / 2) ? __ldcs(p + k) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * kWarp;
+            if (k >= d / 2) break;
+            s = fmaf(v[u].x, v[u].x, s);
+            s = fmaf(v[u].y, v[u].y, s);
+            const __half h0 = __float2half_rn(fminf(fmaxf(v[u].x, -65504.0f), 65504.0f));
+            const __half h1 = __float2half_rn(fminf(fmaxf(v[u].y, -65504.0f), 65504.0f));
+            const float d0 = v[u].x - __half2float(h0), d1 = v[u].y - __half2float(h1);    // exact in fp32 (NaN / inf stay NaN / inf)
+            e = fmaf(d0, d0, e);
+            e = fmaf(d1, d1, e);
+            q[k] = (unsigned)__half_as_ushort(h0) | ((unsigned)__half_as_ushort(h1) << 16);
+        }
+    }
+    norm = warp_sum(s);
+    resid = warp_sum(e) * 1.0000005f;          // the sum itself is rounded: keep the residual norm an upper bound
+}
+
+// fp32 rows -> fp16 copy, |row|^2 and the residual norms; max_resid_bits: running maximum of the residuals' bit patterns.
+// One warp per row.
 __global__ void __launch_bounds__(256)
 rows_to_half_kernel(const float *__restrict__ x, int64_t rows, int d, unsigned short *__restrict__ xh, float *__restrict__ norm,
                     float *__restrict__ resid, unsigned *max_resid_bits)
 {
     const int lane = threadIdx.x & 31;
     for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
-        const float2 *p = reinterpret_cast<const float2 *>(x + r * d);
-        unsigned *q = reinterpret_cast<unsigned *>(xh + r * d);
-        float s = 0.0f, e = 0.0f;
-        // batches of 8 independent 8-byte loads per lane (a whole d = 512 row in flight per warp); the running sums keep
-        // the element order of the plain loop, so the norms do not depend on the batching
-        for (int k0 = lane; k0 < d / 2; k0 += 8 * kWarp) {
-            float2 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int k = k0 + u * kWarp;
-                v[u] = (k < d / 2) ? __ldcs(p + k) : make_float2(0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int k = k0 + u * kWarp;
-                if (k >= d / 2) break;
-                s = fmaf(v[u].x, v[u].x, s);
-                s = fmaf(v[u].y, v[u].y, s);
-                const __half h0 = __float2half_rn(fminf(fmaxf(v[u].x, -65504.0f), 65504.0f));
-                const __half h1 = __float2half_rn(fminf(fmaxf(v[u].y, -65504.0f), 65504.0f));
-                const float d0 = v[u].x - __half2float(h0), d1 = v[u].y - __half2float(h1);    // exact in fp32 (NaN / inf stay NaN / inf)
-                e = fmaf(d0, d0, e);
-                e = fmaf(d1, d1, e);
-                q[k] = (unsigned)__half_as_ushort(h0) | ((unsigned)__half_as_ushort(h1) << 16);
-            }
-        }
-        s = warp_sum(s);
-        e = warp_sum(e) * 1.0000005f;          // the sum itself is rounded: keep the residual norm an upper bound
+        float s, e;
+        warp_row_to_half(x + r * d, d, xh + r * d, s, e);
         if (lane == 0) {
             if (norm) norm[r] = s;
             if (resid) resid[r] = e;
@@ -424,11 +444,12 @@ bool discretize_tc_supported(int64_t R, int d, int M, bool half)
     return d % (half ? 8 : 4) == 0 && d >= 32 && M >= 16 && R >= 1 && encode_tiled_fn() != nullptr;
 }
 
-int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws, cudaStream_t st)
+int launch_codebook_norms(const float *C, int M, int d, const DiscWorkspace &ws, cudaStream_t st, bool half_copy)
 {
     const int padded = (M + 255) / 256 * 256;
     SH_LAUNCH("codebook_norms_kernel", st,
-              codebook_norms_kernel<<<ceil_div(padded, 8), 256, 0, st>>>(C, M, padded, d, ws.cn, (unsigned *)(ws.counters + 2)));
+              codebook_norms_kernel<<<ceil_div(padded, 8), 256, 0, st>>>(C, M, padded, d, ws.cn, (unsigned *)(ws.counters + 2),
+                                                                         half_copy ? ws.cb : nullptr, (unsigned *)(ws.counters + 2) + 1));
     SH_CHECK_LAUNCH();
     return 0;
 }
@@ -504,10 +525,9 @@ int launch_discretize_tc(const float *X, const float *C, int64_t R, int d, int M
     CUtensorMap tmA, tmB;
     if (half) {
         // one pass over the tokens produces the fp16 copy, |x|^2 and the residual norms (the fp32 path needs a pass for |x|^2 anyway)
-        const int g1 = (int)min(ceil_div64(R, 8), (int64_t)sm_count() * 16), g2 = (int)min(ceil_div64(M, 8), (int64_t)sm_count() * 16);
+        // (the codebook's fp16 copy and residual maximum come from launch_codebook_norms(..., half_copy = true))
+        const int g1 = (int)min(ceil_div64(R, 8), (int64_t)sm_count() * 16);
         SH_LAUNCH("rows_to_half_kernel", st, rows_to_half_kernel<<<g1, 256, 0, st>>>(X, R, d, ws.xb, ws.xn, ws.xe, nullptr));
-        SH_CHECK_LAUNCH();
-        SH_LAUNCH("rows_to_half_kernel", st, rows_to_half_kernel<<<g2, 256, 0, st>>>(C, M, d, ws.cb, nullptr, nullptr, (unsigned *)(ws.counters + 2) + 1));
         SH_CHECK_LAUNCH();
         if (make_tmap_f16(&tmA, ws.xb, (uint64_t)d, (uint64_t)R, TC_BM)) return 1;
         if (make_tmap_f16(&tmB, ws.cb, (uint64_t)d, (uint64_t)M, (uint32_t)(BN / b_split))) return 1;

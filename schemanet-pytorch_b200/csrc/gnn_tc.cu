@@ -1716,14 +1716,19 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
     // operand maxima of this forward: reset, then the Linear weights' (every other slot is written by the kernel that
     // produces the operand)
     SH_CHECK_CUDA(cudaMemsetAsync(b.amax, 0, 512, st));
-    {
+    auto param_bounds = [&](cudaStream_t s_) -> int {
         ParamPtrs pp{};
         for (int l = 0; l < p->num_layers; ++l) { pp.w[l] = p->lin_w[l]; pp.gamma[l] = p->ln_w[l]; pp.beta[l] = p->ln_b[l]; }
         pp.emb = p->embedding; pp.fc = p->fc_w; pp.emb_n = (long long)(p->num_codes + 1) * D; pp.layers = p->num_layers;
         const bool wide_tables = D > G_BN && wide_fused(p, G, n_fixed);       // (only that path multiplies the table / fc on the tensor cores)
-        SH_LAUNCH("gnn_param_bounds", st, param_bounds_kernel<<<dim3(wide_tables ? 64 : 16, p->num_layers + (wide_tables ? 2 : 0)), 256, 0, st>>>(pp, D, b.amax));
+        SH_LAUNCH("gnn_param_bounds", s_, param_bounds_kernel<<<dim3(wide_tables ? 64 : 16, p->num_layers + (wide_tables ? 2 : 0)), 256, 0, s_>>>(pp, D, b.amax));
         SH_CHECK_LAUNCH();
-    }
+        return 0;
+    };
+    // (with an auxiliary lane the bounds are its first kernel: their consumers are the GEMMs, which wait for the lane anyway,
+    // and the operand-preparation chain on `st` starts 6-8 us earlier)
+    const bool bounds_on_lane = !wide_fused(p, G, n_fixed) && layer0_fused(p, G, n_fixed);
+    if (!bounds_on_lane && param_bounds(st)) return 1;
     if (wide_fused(p, G, n_fixed)) {
         // P_0 = Emb W_0^T into tab on the tensor cores (no bias here: b_0 is added after the adjacency product), then X_0^T = the
         // rows of P_0 gathered by node id
@@ -1755,6 +1760,7 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
         SH_CHECK_CUDA(cudaEventRecord(lane->fork, st));
         SH_CHECK_CUDA(cudaStreamWaitEvent(ts, lane->fork, 0));
     }
+    if (param_bounds(ts)) return 1;
     // P_0 = Emb W_0^T into tab; with a table tail the same launch also emits T_0 = relu(LN(P_0 + b_0)) into h_rows
     if (launch_rows_linear(p->embedding, p->lin_w[0], p->num_codes + 1, D, b.tab, ts, p->lin_b[0], p->ln_w[0], p->ln_b[0],
                            p->ln_eps, table_tail ? b.h_rows : nullptr))
@@ -1992,7 +1998,7 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
     }
     if (pooled_in_epilogue && fin != nullptr) {
         SH_LAUNCH("gnn_pool_fc", st,
-                  pool_groups_fc_kernel<<<dim3(G, G >= 1024 ? 1 : 8), 256, (size_t)D * sizeof(float), st>>>(
+                  pool_groups_fc_kernel<<<dim3(G, G >= 1024 ? 1 : (G >= 192 ? 4 : 8)), 256, (size_t)D * sizeof(float), st>>>(
                       b.pool_groups, row_sizes, n_fixed, D, table_tail ? b.pool_extra : nullptr, fin->mean_div, p->fc_w, p->fc_b, fin->out));
         fin->done = true;
     } else if (pooled_in_epilogue) {

@@ -26,4 +26,4 @@ PY
   done
 done
 cp $D/variant_${AB_FINAL:-b}.so $D/libschemahead.so
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "gnn or class or cfg or golden or head" 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "gnn or class or cfg or golden or head or discretize" 2>&1 | tail -2
