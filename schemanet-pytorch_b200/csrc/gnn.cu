@@ -278,52 +278,81 @@ pool_fc_kernel(const float *__restrict__ partial, int chunks, int D, int n_fixed
 // optionally also act[r, :] = relu(LayerNorm(out[r, :] + bias)) (one layer of the per-code activation tables, gnn_tc.cu).
 // (The generic tiled GEMM launches only ~18 CTAs for this shape and took 0.11 ms; a warp-per-output version with shuffle
 // reductions 0.028 ms; thread-per-output streaming its own W row 0.018 ms, L1-tag bound on 32 lines per request.)
-// kRows rows per CTA staged in shared memory; W goes through shared memory in 32-column slabs, read with coalesced 128 B
-// row segments and stored transposed (stride 257: conflict-free both ways); thread o owns output feature o for all kRows
-// rows -- kRows independent FMA chains per thread, no reductions.
+// kRows rows per CTA staged in shared memory; thread o owns output feature o for all kRows rows -- kRows independent FMA
+// chains per thread, no reductions.  W streams through a 3-stage shared-memory ring in 32-column slabs by cp.async (16-byte
+// pieces, rows padded to 36 floats: the 16-byte reads of a quarter-warp hit 32 distinct banks).  With the previous
+// register-staged, one-slab-ahead pipeline every slab exposed an L2 round trip (8 slabs: 20 us for 134 MFLOP); two slabs
+// are now in flight while one is used.  The products of an output are folded in ascending k as before.
+constexpr int kRlPitch = 36, kRlStages = 3;
+__device__ __forceinline__ void rl_cp_async16(float *dst_smem, const float *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
 template <int kRows>
 __global__ void __launch_bounds__(256)
 rows_linear_kernel(const float *__restrict__ A, const float *__restrict__ W, int rows, int D, float *__restrict__ out,
                    const float *__restrict__ bias, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
                    float *__restrict__ act)
 {
-    __shared__ __align__(16) float As[kRows][256];
-    __shared__ float Ws[32][257];
+    extern __shared__ __align__(16) float rl_smem[];
+    float (*As)[256] = reinterpret_cast<float (*)[256]>(rl_smem);                  // [kRows][256]
+    float *Wring = rl_smem + kRows * 256;                                          // [kRlStages][256][kRlPitch]
     __shared__ float red[8][kRows];
     const int r0 = blockIdx.x * kRows, o = threadIdx.x, lane = o & 31, warp = o >> 5;
-    for (int i = 0; i < kRows; ++i) As[i][o] = (o < D && r0 + i < rows) ? __ldg(A + (size_t)(r0 + i) * D + o) : 0.0f;
+    // slab k0 of W -> stage: 256 rows x 8 pieces of 16 bytes, 8 pieces per thread (rows >= D: never read by a live thread)
+    auto issue = [&](int k0, int stage) {
+        float *dst = Wring + (size_t)stage * 256 * kRlPitch;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = j * 256 + o, row = c >> 3, piece = c & 7;
+            if (row < D) rl_cp_async16(dst + row * kRlPitch + piece * 4, W + (size_t)row * D + k0 + piece * 4);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int slabs = D / 32;
+    for (int sidx = 0; sidx < kRlStages - 1; ++sidx) {
+        if (sidx < slabs) issue(sidx * 32, sidx);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    {
+        float a[kRows];
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) a[i] = (o < D && r0 + i < rows) ? __ldg(A + (size_t)(r0 + i) * D + o) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) As[i][o] = a[i];
+    }
     float acc[kRows];
 #pragma unroll
     for (int i = 0; i < kRows; ++i) acc[i] = 0.0f;
-    // W slabs are software-pipelined: the next slab's 8 float4 per thread are in flight while the current one is used
-    float4 wn[8];
-    auto fetch = [&](int k0) {
+    for (int it = 0; it < slabs; ++it) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kRlStages - 2) : "memory");      // slab `it` has landed (this thread's pieces)
+        __syncthreads();                      // ... everyone's pieces; slab it - 1 is consumed by all (first pass: As visible)
+        if (it + kRlStages - 1 < slabs) issue((it + kRlStages - 1) * 32, (it + kRlStages - 1) % kRlStages);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const float *wrow = Wring + (size_t)(it % kRlStages) * 256 * kRlPitch + o * kRlPitch;
+        const int k0 = it * 32;
+        // the shared-memory reads of step k4 + 1 are issued before the FMAs of step k4 (two warps per scheduler do not hide
+        // the read latency by themselves: 28 % of the kernel's stall samples were FMAs waiting for their operands)
+        float4 wn = *reinterpret_cast<const float4 *>(wrow), avn[kRows];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {         // rows j*32 + o/8 of W, float4 (o % 8) of the slab
-            const int row = j * 32 + (o >> 3);
-            wn[j] = row < D ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)row * D + k0 + (o & 7) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    fetch(0);
-    for (int k0 = 0; k0 < D; k0 += 32) {
-        __syncthreads();                      // previous slab consumed (first pass: As visible)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int row = j * 32 + (o >> 3), c4 = (o & 7) * 4;
-            Ws[c4 + 0][row] = wn[j].x; Ws[c4 + 1][row] = wn[j].y; Ws[c4 + 2][row] = wn[j].z; Ws[c4 + 3][row] = wn[j].w;
-        }
-        if (k0 + 32 < D) fetch(k0 + 32);
-        __syncthreads();
+        for (int i = 0; i < kRows; ++i) avn[i] = *reinterpret_cast<const float4 *>(&As[i][k0]);
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-            const float w0 = Ws[4 * k4][o], w1 = Ws[4 * k4 + 1][o], w2 = Ws[4 * k4 + 2][o], w3 = Ws[4 * k4 + 3][o];
+            const float4 w = wn;
+            float4 av[kRows];
+#pragma unroll
+            for (int i = 0; i < kRows; ++i) av[i] = avn[i];
+            if (k4 + 1 < 8) {
+                wn = *reinterpret_cast<const float4 *>(wrow + 4 * (k4 + 1));
+#pragma unroll
+                for (int i = 0; i < kRows; ++i) avn[i] = *reinterpret_cast<const float4 *>(&As[i][k0 + 4 * (k4 + 1)]);
+            }
 #pragma unroll
             for (int i = 0; i < kRows; ++i) {
-                const float4 av = *reinterpret_cast<const float4 *>(&As[i][k0 + 4 * k4]);
-                acc[i] = fmaf(av.x, w0, acc[i]);
-                acc[i] = fmaf(av.y, w1, acc[i]);
-                acc[i] = fmaf(av.z, w2, acc[i]);
-                acc[i] = fmaf(av.w, w3, acc[i]);
+                acc[i] = fmaf(av[i].x, w.x, acc[i]);
+                acc[i] = fmaf(av[i].y, w.y, acc[i]);
+                acc[i] = fmaf(av[i].z, w.z, acc[i]);
+                acc[i] = fmaf(av[i].w, w.w, acc[i]);
             }
         }
     }
@@ -377,8 +406,15 @@ int launch_rows_linear(const float *A, const float *W, int rows, int D, float *o
 {
     SH_REQUIRE(D <= 256 && D % 32 == 0, "rows_linear: D <= 256, D %% 32 == 0 expected");
     SH_REQUIRE(out || act, "rows_linear: no output");
+    SH_REQUIRE((((uintptr_t)A | (uintptr_t)W) & 15) == 0, "rows_linear: operands must be 16-byte aligned");
+    constexpr size_t smem = (size_t)(8 * 256 + kRlStages * 256 * kRlPitch) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        SH_CHECK_CUDA(cudaFuncSetAttribute(rows_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
     SH_LAUNCH("gnn_embed_table_linear", st,
-              rows_linear_kernel<8><<<ceil_div(rows, 8), 256, 0, st>>>(A, W, rows, D, out, bias, gamma, beta, eps, act));
+              rows_linear_kernel<8><<<ceil_div(rows, 8), 256, smem, st>>>(A, W, rows, D, out, bias, gamma, beta, eps, act));
     SH_CHECK_LAUNCH();
     return 0;
 }
