@@ -323,10 +323,22 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         tma_load_3d(s, &tmA, &full[stage], kb * G_BK, mb * G_BM, g);
                     }
                     __syncwarp();                                           // the slot is free: every lane may write into it
-                    const int k = kb * G_BK + lane;
-                    const int row = k < kGatherMaxNodes ? s_ids[k] : a.bg_zero_row;
-                    const float *src = a.bg_table + (size_t)row * a.N_total + nb * G_BN + rank * P::kBRows;
-                    bulk_copy_g2s(s + kABytes + lane * (P::kBRows * 4), src, P::kBRows * 4, &full[stage]);
+                    if (a.debug & 8) {
+                        // (A/B, SCHEMANET_GEMM_DEBUG=8) one 1-D bulk copy per node: 32 copy operations per k-block; the
+                        // producer, not the conversion, then bounds the launch (r02_experiments.md)
+                        const int k = kb * G_BK + lane;
+                        const int row = k < kGatherMaxNodes ? s_ids[k] : a.bg_zero_row;
+                        const float *src = a.bg_table + (size_t)row * a.N_total + nb * G_BN + rank * P::kBRows;
+                        bulk_copy_g2s(s + kABytes + lane * (P::kBRows * 4), src, P::kBRows * 4, &full[stage]);
+                    } else if (lane < G_BK / 4) {
+                        // TMA gather: four table rows per operation (tmB is the 2-D map of the table, box {kBRows, 1})
+                        const int k = kb * G_BK + 4 * lane;
+                        int r[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) r[u] = k + u < kGatherMaxNodes ? s_ids[k + u] : a.bg_zero_row;
+                        tma_gather4_2d(s + kABytes + 4 * lane * (P::kBRows * 4), &tmB, &full[stage], nb * G_BN + rank * P::kBRows,
+                                       r[0], r[1], r[2], r[3]);
+                    }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             TILE_LOOP_END
@@ -1665,6 +1677,22 @@ static int tmap3(CUtensorMap *m, const float *p, uint64_t cols, uint64_t rows, u
     return 0;
 }
 
+// 2-D map over a row-major fp32 table [rows, cols] with a box of {box_cols, 1} and no swizzle: the form tile::gather4 loads take
+static int tmap_rows(CUtensorMap *m, const float *p, uint64_t cols, uint64_t rows, uint32_t box_cols)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    SH_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 4};
+    cuuint32_t box[2] = {box_cols, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SH_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (gather) failed with CUresult %d", (int)r);
+    return 0;
+}
+
 // All GNN layers given a prepared adjacency in b.adj.  k_sizes: active size per graph for the adjacency GEMM
 // (null = n_fixed); identity_tail: see GemmTcArgs; row_sizes: real rows per graph for masking (null = all).
 static bool layer0_fused(const sh_gnn_params *p, int G, int n_fixed)
@@ -1852,6 +1880,9 @@ static int run_layers_wide(const sh_gnn_params *p, int G, int n_fixed, const int
             if (n_fixed <= kGatherMaxNodes) {     // B = rows of the table P_0 gathered by node code inside the GEMM
                 a.bg_table = b.tab; a.bg_ids = ids; a.bg_ld = ld_ids; a.bg_sizes = row_sizes;
                 a.bg_zero_row = p->num_codes;          // Emb[num_codes] = 0 (padding_idx, gnn.py:66-70) -> P_0[num_codes] = 0
+                // the B map of this launch is the table itself, for the producer's TMA gather (box {B columns of a CTA, 1 row})
+                if (tmap_rows(&m1[1], b.tab, D, p->num_codes + 1, G_BN)) return 1;
+                if (tmap_rows(&m1p[1], b.tab, D, p->num_codes + 1, G_BN / 2)) return 1;
             }
             if (last) { a.out_rows = b.h_rows; if (launch_gemm3x<EPI_Z_ROWS_STATS>(m1, m1p, a, "gnn_adj_z_tc", st)) return 1; }
             else { a.out_t = xout; if (launch_gemm3x<EPI_Z_T_STATS>(m1, m1p, a, "gnn_adj_z_tc", st)) return 1; }

@@ -100,6 +100,14 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// TMA gather (sm_100): four arbitrary rows r0..r3 of a 2-D tensor (map encoded with a box of {width, 1}), columns
+// [col, col + width), land as four consecutive rows at dst; completion on an mbarrier like any TMA box
+__device__ __forceinline__ void tma_gather4_2d(void *dst, const CUtensorMap *m, uint64_t *bar, int col, int r0, int r1, int r2, int r3)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+                 : "memory");
+}
 // generic-proxy writes to shared memory -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
