@@ -292,7 +292,7 @@ template <int kRows>
 __global__ void __launch_bounds__(256)
 rows_linear_kernel(const float *__restrict__ A, const float *__restrict__ W, int rows, int D, float *__restrict__ out,
                    const float *__restrict__ bias, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
-                   float *__restrict__ act)
+                   float *__restrict__ act, unsigned *__restrict__ amax_out)
 {
     extern __shared__ __align__(16) float rl_smem[];
     float (*As)[256] = reinterpret_cast<float (*)[256]>(rl_smem);                  // [kRows][256]
@@ -362,6 +362,14 @@ rows_linear_kernel(const float *__restrict__ A, const float *__restrict__ W, int
         for (int i = 0; i < kRows; ++i)
             if (r0 + i < rows) out[(size_t)(r0 + i) * D + o] = acc[i];
     }
+    if (amax_out != nullptr) {      // largest magnitude written to `out` (bit pattern; the consumer scales its operand by it)
+        float mx = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kRows; ++i)
+            if (live && r0 + i < rows) mx = fmaxf(mx, fabsf(acc[i]));
+        mx = warp_max(mx);
+        if (lane == 0 && !(mx == 0.0f)) atomicMax(amax_out, __float_as_uint(mx));      // NaN compares above +inf
+    }
     if (act == nullptr) return;
     // LayerNorm over the D features of each row (two-pass: mean, then centred variance), block reductions via `red`
     const float bo = live ? bias[o] : 0.0f;
@@ -402,7 +410,7 @@ rows_linear_kernel(const float *__restrict__ A, const float *__restrict__ W, int
 }
 
 int launch_rows_linear(const float *A, const float *W, int rows, int D, float *out, cudaStream_t st, const float *bias,
-                       const float *gamma, const float *beta, float eps, float *act)
+                       const float *gamma, const float *beta, float eps, float *act, unsigned *amax_out)
 {
     SH_REQUIRE(D <= 256 && D % 32 == 0, "rows_linear: D <= 256, D %% 32 == 0 expected");
     SH_REQUIRE(out || act, "rows_linear: no output");
@@ -414,7 +422,7 @@ int launch_rows_linear(const float *A, const float *W, int rows, int D, float *o
         configured = true;
     }
     SH_LAUNCH("gnn_embed_table_linear", st,
-              rows_linear_kernel<8><<<ceil_div(rows, 8), 256, smem, st>>>(A, W, rows, D, out, bias, gamma, beta, eps, act));
+              rows_linear_kernel<8><<<ceil_div(rows, 8), 256, smem, st>>>(A, W, rows, D, out, bias, gamma, beta, eps, act, amax_out));
     SH_CHECK_LAUNCH();
     return 0;
 }

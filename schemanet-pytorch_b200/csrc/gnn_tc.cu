@@ -102,7 +102,7 @@ struct GemmTcArgs {
     // the gathered table rows is never written): the producer warp issues one bulk copy per node (its slice of a table row,
     // completing on the stage's mbarrier like a TMA box); the landing tile is [k][f] and the transform warps read it
     // transposed.  bg_table [rows, N_total] fp32, bg_ids [G, bg_ld] node codes, bg_sizes [G] live nodes per graph (null:
-    // rows_per_graph); nodes beyond read bg_zero_row, a table row that is all zeros (the padding code's)
+    // rows_per_graph); nodes beyond read bg_zero_row, a table row that is all zeros (written by tables_begin behind the table)
     const float *bg_table;
     const int64_t *bg_ids;
     const int32_t *bg_sizes;
@@ -1551,7 +1551,7 @@ static TcBuffers carve_tc(void *base, int G, int n_fixed, int D)
     b.xt = (float *)(p + off); off += xt_b;
     b.xt2 = (float *)(p + off); off += xt_b;
     b.y = (float *)(p + off); off += y_b;
-    b.tab = (float *)(p + off); off += y_b;
+    b.tab = (float *)(p + off); off += y_b + al256((size_t)D * 4);      // (+ the all-zero row the in-GEMM gather reads for absent nodes)
     b.h_rows = (float *)(p + off); off += y_b;
     b.n_act = (int32_t *)(p + off); off += al256((size_t)G * 4);
     b.old_of_new = (int32_t *)(p + off); off += al256((size_t)G * n_fixed * 4);
@@ -1699,6 +1699,14 @@ static bool layer0_fused(const sh_gnn_params *p, int G, int n_fixed)
 {
     return p->embed_dim == G_BN && (int64_t)(p->num_codes + 1) <= (int64_t)G * n_fixed;
 }
+// embed_dim = 256 with the layer-0 shortcut: the B operand of the layer-0 adjacency GEMM (rows of P_0 by node code) is gathered by
+// the GEMM's producer (TMA tile::gather4) instead of being materialised as X_0^T by embed_gather_t_kernel.
+// SCHEMANET_EMBED_GATHER_KERNEL=1 keeps the kernel (A/B).
+static bool narrow_gather(const sh_gnn_params *p, int G, int n_fixed)
+{
+    static const bool off = getenv("SCHEMANET_EMBED_GATHER_KERNEL") != nullptr;
+    return !off && layer0_fused(p, G, n_fixed) && n_fixed <= kGatherMaxNodes;
+}
 // embed_dim > 256 (ImageNet configuration: 1024): the same layer-0 shortcut -- the first Linear is applied to the (M+1)-row
 // embedding table, on the tensor cores -- and LayerNorm applied by the consumers of z (EPI_Z_*_STATS), see run_layers_wide
 static bool wide_fused(const sh_gnn_params *p, int G, int n_fixed)
@@ -1744,6 +1752,9 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
     // operand maxima of this forward: reset, then the Linear weights' (every other slot is written by the kernel that
     // produces the operand)
     SH_CHECK_CUDA(cudaMemsetAsync(b.amax, 0, 512, st));
+    // row M + 1 of the table buffer: zeros, what the in-GEMM gather of the layer-0 operand reads for nodes past a graph's size
+    if (layer0_fused(p, G, n_fixed) || wide_fused(p, G, n_fixed))       // (otherwise there is no table: it may not even fit)
+        SH_CHECK_CUDA(cudaMemsetAsync(b.tab + (size_t)(p->num_codes + 1) * D, 0, (size_t)D * 4, st));
     auto param_bounds = [&](cudaStream_t s_) -> int {
         ParamPtrs pp{};
         for (int l = 0; l < p->num_layers; ++l) { pp.w[l] = p->lin_w[l]; pp.gamma[l] = p->ln_w[l]; pp.beta[l] = p->ln_b[l]; }
@@ -1791,7 +1802,7 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
     if (param_bounds(ts)) return 1;
     // P_0 = Emb W_0^T into tab; with a table tail the same launch also emits T_0 = relu(LN(P_0 + b_0)) into h_rows
     if (launch_rows_linear(p->embedding, p->lin_w[0], p->num_codes + 1, D, b.tab, ts, p->lin_b[0], p->ln_w[0], p->ln_b[0],
-                           p->ln_eps, table_tail ? b.h_rows : nullptr))
+                           p->ln_eps, table_tail ? b.h_rows : nullptr, narrow_gather(p, G, n_fixed) ? b.amax + AM_X : nullptr))
         return 1;
     if (table_tail) {
         // T_l ping-pongs between h_rows and y: both are free until the GEMMs reach them, and the pooled sums of the
@@ -1806,7 +1817,7 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
         SH_LAUNCH("gnn_pool_table_rows", ts, pool_table_rows_kernel<<<dim3(G, kTableSlices), 256, (size_t)ceil_div(n_fixed, kTableSlices) * 8, ts>>>(cur, ids, vertex_w, row_sizes, n_fixed, D, b.pool_extra));
         SH_CHECK_LAUNCH();
     }
-    {
+    if (!narrow_gather(p, G, n_fixed)) {
         // X_0^T of the fused layer 0 (rows of P_0 gathered by node id): L2-write bound, it also runs under the HBM-read-bound
         // operand preparation
         dim3 grid2(ceil_div(b.ldk, 32), ceil_div(D, 256), G);
@@ -1879,10 +1890,10 @@ static int run_layers_wide(const sh_gnn_params *p, int G, int n_fixed, const int
             a.amax_b = b.amax + AM_X; a.row_sizes = row_sizes; a.bias = p->lin_b[0];
             if (n_fixed <= kGatherMaxNodes) {     // B = rows of the table P_0 gathered by node code inside the GEMM
                 a.bg_table = b.tab; a.bg_ids = ids; a.bg_ld = ld_ids; a.bg_sizes = row_sizes;
-                a.bg_zero_row = p->num_codes;          // Emb[num_codes] = 0 (padding_idx, gnn.py:66-70) -> P_0[num_codes] = 0
+                a.bg_zero_row = p->num_codes + 1;      // the explicit zero row behind the table (tables_begin)
                 // the B map of this launch is the table itself, for the producer's TMA gather (box {B columns of a CTA, 1 row})
-                if (tmap_rows(&m1[1], b.tab, D, p->num_codes + 1, G_BN)) return 1;
-                if (tmap_rows(&m1p[1], b.tab, D, p->num_codes + 1, G_BN / 2)) return 1;
+                if (tmap_rows(&m1[1], b.tab, D, p->num_codes + 2, G_BN)) return 1;
+                if (tmap_rows(&m1p[1], b.tab, D, p->num_codes + 2, G_BN / 2)) return 1;
             }
             if (last) { a.out_rows = b.h_rows; if (launch_gemm3x<EPI_Z_ROWS_STATS>(m1, m1p, a, "gnn_adj_z_tc", st)) return 1; }
             else { a.out_t = xout; if (launch_gemm3x<EPI_Z_T_STATS>(m1, m1p, a, "gnn_adj_z_tc", st)) return 1; }
@@ -1976,6 +1987,13 @@ static int run_layers_tc(const sh_gnn_params *p, int G, int n_fixed, const int32
         if (l == 0 && fuse0) {
             // H1 = relu(LN(Adj (X0 W0^T) + b0)) in one kernel
             a.row_sizes = row_sizes;
+            if (narrow_gather(p, G, n_fixed)) {
+                // B = rows of P_0 gathered by node code by the producer (nodes >= row_sizes[g]: the table's zero row)
+                a.bg_table = b.tab; a.bg_ids = ids; a.bg_ld = ld_ids; a.bg_sizes = row_sizes;
+                a.bg_zero_row = p->num_codes + 1;      // the explicit zero row behind the table (tables_begin)
+                if (tmap_rows(&m1[1], b.tab, D, p->num_codes + 2, G_BN)) return 1;
+                if (tmap_rows(&m1p[1], b.tab, D, p->num_codes + 2, G_BN / 2)) return 1;
+            }
             a.bias = p->lin_b[0]; a.gamma = p->ln_w[0]; a.beta = p->ln_b[0]; a.eps = p->ln_eps;
             a.out_t = xout; a.ldk = ldk; a.out_rows = b.h_rows; a.amax_out = b.amax + AM_X + l + 1;
             if (last) { if (launch_gemm3x<EPI_LN_RELU_ROWS, 8>(m1, m1p, a, "gnn_adj_ln_tc", st)) return 1; }

@@ -44,6 +44,7 @@ int launch_class_edges(float *edge_weights, const float *class_vertices, int K, 
 // out[rows, D] = A[rows, D] W^T with W [D, D] (fp32 CUDA-core GEMM from gnn.cu; used for the embedding-table shortcut)
 // act (optional): relu(LayerNorm(out + bias)) of the same rows, fused
 int launch_rows_linear(const float *A, const float *W, int rows, int D, float *out, cudaStream_t st, const float *bias = nullptr,
-                       const float *gamma = nullptr, const float *beta = nullptr, float eps = 0.0f, float *act = nullptr);
+                       const float *gamma = nullptr, const float *beta = nullptr, float eps = 0.0f, float *act = nullptr,
+                       unsigned *amax_out = nullptr);      // amax_out: atomicMax of the bit patterns of |out|
 
 }  // namespace sh
