@@ -521,7 +521,8 @@ def test_class_side_large_tile_path():
 
 @pytest.mark.parametrize("K,Vc,D,thr,rsl", [(4, 1024, 256, 0.001, False), (3, 500, 256, 0.001, True), (2, 296, 512, 0.0034, False),
                                             (3, 264, 256, None, False), (2, 301, 256, 0.0033, False),
-                                            (3, 264, 256, 0.5, False)])     # 0.5: every vertex pruned (adjacency = I)
+                                            (3, 264, 256, 0.5, False),      # 0.5: every vertex pruned (adjacency = I)
+                                            (2, 1056, 256, 0.001, False)])  # Vc > 1024: generic atlas kernel, X0^T by the gather kernel
 def test_class_side_fused_equals_atlas_then_gnn(K, Vc, D, thr, rsl):
     """sh_dev_class_side on the tensor-core path feeds the compacted, normalised edges straight into the adjacency
     operand.  It must return bit-identical class embeddings whether or not the full class_edges tensor is asked for,
