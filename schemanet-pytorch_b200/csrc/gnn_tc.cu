@@ -1814,6 +1814,11 @@ static int tables_begin(const sh_gnn_params *p, int G, int n_fixed, const int32_
                 return 1;
             float *t = cur; cur = nxt; nxt = t;
         }
+        static bool pool_smem_set = false;           // (Vc up to 65535: 64 KB of codes + weights per slice, above the 48 KB default)
+        if (!pool_smem_set) {
+            SH_CHECK_CUDA(cudaFuncSetAttribute(pool_table_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            pool_smem_set = true;
+        }
         SH_LAUNCH("gnn_pool_table_rows", ts, pool_table_rows_kernel<<<dim3(G, kTableSlices), 256, (size_t)ceil_div(n_fixed, kTableSlices) * 8, ts>>>(cur, ids, vertex_w, row_sizes, n_fixed, D, b.pool_extra));
         SH_CHECK_LAUNCH();
     }
