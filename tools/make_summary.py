@@ -72,6 +72,7 @@ out += ["\n## Files\n",
         "* r02_launches_bench_cfg2.txt -- ncu launch list of `bench.py --steps 2 --warmup 1` (cold-cache, serialised: compare shares)",
         "* r02_ncu_full_kernels.txt, r02_ncu_traffic.json -- `ncu --set full` of the hot kernels (tools/ncu_summary.py)",
         "* r02_compute_sanitizer.txt -- memcheck (26 parity tests), racecheck and synccheck (smoke, wide fused path, fused class side): 0 errors / 0 hazards",
+        "* r02_sass_mnemonics.txt -- tcgen05 / TMA (incl. `UTMALDG.2D.GATHER4`) / TMEM / cp.async mnemonic counts of the shipped library",
         "* r02_experiments.md -- variants measured this round, kept or not, with their numbers"]
 open(os.path.join(P, "r02_summary.md"), "w").write("\n".join(out) + "\n")
 print("wrote profiles/r02_summary.md")
